@@ -1,0 +1,34 @@
+"""B200-native distributed embeddings.
+
+Public API (capability parity with ``distributed_embeddings/__init__.py:17-27`` of the reference):
+``Embedding``, ``IntegerLookup``, ``ConcatOneHotEmbedding``, ``embedding_lookup``,
+``DistributedEmbedding``, ``DistEmbeddingStrategy``, ``broadcast_variables``,
+``DistributedGradientTape``, ``DistributedOptimizer``, ``BroadcastGlobalVariablesCallback``;
+``dist_model_parallel`` is importable as a namespace (``from distributed_embeddings_b200 import
+dist_model_parallel as dmp``).
+"""
+from .version import __version__
+from .layers.embedding import ConcatOneHotEmbedding, Embedding, IntegerLookup
+from .ops.embedding_lookup_ops import (embedding_lookup, integer_lookup, read_var_no_copy,
+                                       row_to_split)
+from .ops.ragged import RaggedIds, SparseIds
+from .parallel import dist_model_parallel
+from .parallel.comm import CommContext
+from .parallel.dist_model_parallel import DistributedEmbedding, broadcast_variables
+from .parallel.hybrid import (BroadcastGlobalVariablesCallback, DistributedGradientTape,
+                              DistributedOptimizer, GradBucket, allreduce_gradients)
+from .parallel.strategy import DistEmbeddingStrategy
+
+# the reference exposes the hybrid helpers through the dist_model_parallel module
+dist_model_parallel.DistributedGradientTape = DistributedGradientTape
+dist_model_parallel.DistributedOptimizer = DistributedOptimizer
+dist_model_parallel.BroadcastGlobalVariablesCallback = BroadcastGlobalVariablesCallback
+dist_model_parallel.allreduce_gradients = allreduce_gradients
+
+__all__ = [
+    "Embedding", "IntegerLookup", "ConcatOneHotEmbedding", "embedding_lookup", "integer_lookup",
+    "read_var_no_copy", "row_to_split", "RaggedIds", "SparseIds", "DistributedEmbedding",
+    "DistEmbeddingStrategy", "broadcast_variables", "DistributedGradientTape",
+    "DistributedOptimizer", "BroadcastGlobalVariablesCallback", "GradBucket",
+    "allreduce_gradients", "CommContext", "dist_model_parallel", "__version__"
+]

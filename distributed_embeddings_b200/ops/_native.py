@@ -1,0 +1,98 @@
+"""Loader for the native sm_100a extension and numpy mirrors of its descriptor structs."""
+from __future__ import annotations
+
+import os
+import threading
+
+import numpy as np
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO_PATH = os.path.join(_PKG_DIR, "_C.so")
+
+_lock = threading.Lock()
+_loaded = False
+_error = None
+
+# mirrors of de::InputDesc / de::TableDesc (ops/csrc/de_b200.h); sizes are checked at load time
+INPUT_DESC = np.dtype([
+    ("table", "<u8"),
+    ("ids", "<u8"),
+    ("offsets", "<u8"),
+    ("ids_off", "<i8"),
+    ("id_shift", "<i8"),
+    ("sub_rows", "<i8"),
+    ("row_base", "<i8"),
+    ("width", "<i4"),
+    ("hotness", "<i4"),
+    ("dst_col", "<i4"),
+    ("combiner", "<i4"),
+    ("local_table", "<i4"),
+    ("pad0", "<i4"),
+    ("item_off", "<i8"),
+    ("pad1", "<i8"),
+])
+TABLE_DESC = np.dtype([
+    ("weight", "<u8"),
+    ("state0", "<u8"),
+    ("state1", "<u8"),
+    ("rows", "<i8"),
+    ("key_base", "<i8"),
+    ("width", "<i4"),
+    ("pad", "<i4"),
+])
+
+OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_ADAM, OPT_EMIT = 0, 1, 2, 3, 4
+MAX_PEERS = 16
+
+
+def load(required: bool = False) -> bool:
+  """Load ``_C.so`` once.  Returns True when the native ops are available."""
+  global _loaded, _error
+  if _loaded:
+    return True
+  with _lock:
+    if _loaded:
+      return True
+    if _error is not None and not required:
+      return False
+    try:
+      if not os.path.exists(SO_PATH):
+        raise FileNotFoundError(
+            f"{SO_PATH} is missing - run `python -m distributed_embeddings_b200.ops._build` "
+            "(or `make`) to compile the sm_100a kernels")
+      torch.ops.load_library(SO_PATH)
+      sizes = list(torch.ops.de_b200.struct_sizes())
+      if sizes[0] != INPUT_DESC.itemsize or sizes[1] != TABLE_DESC.itemsize or sizes[2] != MAX_PEERS:
+        raise RuntimeError(f"descriptor layout mismatch: native {sizes} vs python "
+                           f"{[INPUT_DESC.itemsize, TABLE_DESC.itemsize, MAX_PEERS]}")
+      _loaded = True
+      return True
+    except Exception as e:  # pylint: disable=broad-except
+      _error = e
+      if required:
+        raise
+      return False
+
+
+def available() -> bool:
+  return load(required=False)
+
+
+def require():
+  """Fail loudly when a CUDA tensor reaches an op but the extension is missing."""
+  if not load(required=False):
+    raise RuntimeError(
+        "distributed_embeddings_b200: the native sm_100a extension is required for CUDA tensors "
+        f"but could not be loaded ({_error!r}). There is no eager fallback on GPU.")
+  return torch.ops.de_b200
+
+
+def ops():
+  return require()
+
+
+def upload_struct_array(arr: np.ndarray, device) -> torch.Tensor:
+  """Copy a numpy struct array to the device as raw bytes."""
+  raw = torch.from_numpy(np.frombuffer(arr.tobytes(), dtype=np.uint8).copy())
+  return raw.to(device)

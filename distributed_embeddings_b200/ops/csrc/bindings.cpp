@@ -1,0 +1,500 @@
+// TORCH_LIBRARY registration of the native ops (namespace de_b200) and the symmetric-memory
+// runtime (cudaMalloc + CUDA IPC peer mapping).  Compiled with the host compiler only; the
+// kernels live in the .cu files behind the plain C++ launchers of de_b200.h.
+//
+// Capability parity: op schemas + OpKernel classes of the reference
+// (cc/ops/embedding_lookup_ops.cc:24-101, cc/kernels/embedding_lookup_kernels.cc:28-187).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <cuda_runtime.h>
+#include <torch/library.h>
+#include <torch/torch.h>
+
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "de_b200.h"
+
+namespace {
+
+using at::Tensor;
+
+#define DE_CUDA_CHECK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    TORCH_CHECK(_e == cudaSuccess, "CUDA error in " #expr ": ", cudaGetErrorString(_e)); \
+  } while (0)
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+int sm_count() {
+  static int cached = -1;
+  if (cached < 0) cached = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  return cached;
+}
+
+de::PeerPtrs to_peers(at::IntArrayRef ptrs) {
+  TORCH_CHECK(ptrs.size() <= de::kMaxPeers, "at most ", de::kMaxPeers, " peers are supported");
+  de::PeerPtrs p;
+  std::memset(&p, 0, sizeof(p));
+  for (size_t i = 0; i < ptrs.size(); ++i) p.p[i] = reinterpret_cast<void*>(ptrs[i]);
+  return p;
+}
+
+void check_launch() {
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "kernel launch failed: ", cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------ descriptor-driven ops
+std::vector<int64_t> struct_sizes() {
+  return {static_cast<int64_t>(sizeof(de::InputDesc)), static_cast<int64_t>(sizeof(de::TableDesc)),
+          static_cast<int64_t>(de::kMaxPeers)};
+}
+
+void lookup_fwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
+                int64_t dst_batch, int64_t dst_stride, at::IntArrayRef src_ptrs,
+                at::IntArrayRef dst_ptrs, int64_t rot, bool ids64, bool out_bf16, bool vec4) {
+  TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
+  c10::cuda::CUDAGuard guard(descs.device());
+  de::launch_lookup_fwd(reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
+                        static_cast<int>(n_inputs), batch, src_batch, dst_batch, dst_stride,
+                        to_peers(src_ptrs), to_peers(dst_ptrs), static_cast<int>(rot), ids64,
+                        out_bf16, vec4, sm_count(), cur_stream());
+  check_launch();
+}
+
+void scatter_add_bwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
+                     int64_t grad_batch, int64_t grad_stride, at::IntArrayRef src_ptrs,
+                     at::IntArrayRef grad_ptrs, int64_t rot, double scale, int64_t scale_ptr,
+                     bool ids64, bool grad_bf16, bool vec4) {
+  TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
+  c10::cuda::CUDAGuard guard(descs.device());
+  de::launch_scatter_add_bwd(reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
+                             static_cast<int>(n_inputs), batch, src_batch, grad_batch, grad_stride,
+                             to_peers(src_ptrs), to_peers(grad_ptrs), static_cast<int>(rot),
+                             static_cast<float>(scale), reinterpret_cast<const float*>(scale_ptr),
+                             ids64, grad_bf16, vec4, sm_count(), cur_stream());
+  check_launch();
+}
+
+int bit_length(int64_t v) {
+  int b = 0;
+  while (v > 0) {
+    ++b;
+    v >>= 1;
+  }
+  return b < 1 ? 1 : b;
+}
+
+// Build (row key, item) pairs for every looked-up id, sort by key, and find the unique rows.
+// Returns (sorted_keys, sorted_items, seg_start, n_unique[1]); nothing is copied to the host.
+std::tuple<Tensor, Tensor, Tensor, Tensor> sort_items(const Tensor& descs, const Tensor& tables,
+                                                      int64_t n_tables, int64_t n_inputs,
+                                                      int64_t batch, int64_t src_batch,
+                                                      at::IntArrayRef src_ptrs, bool ids64,
+                                                      int64_t n_items, int64_t total_rows) {
+  TORCH_CHECK(descs.is_cuda() && tables.is_cuda());
+  c10::cuda::CUDAGuard guard(descs.device());
+  auto stream = cur_stream();
+  auto i64 = at::TensorOptions().device(descs.device()).dtype(at::kLong);
+  auto i32 = at::TensorOptions().device(descs.device()).dtype(at::kInt);
+  Tensor keys = at::empty({n_items}, i64), keys_sorted = at::empty({n_items}, i64);
+  Tensor items = at::empty({n_items}, i32), items_sorted = at::empty({n_items}, i32);
+  Tensor seg_start = at::empty({n_items + 1}, i64);
+  Tensor n_unique = at::zeros({1}, i64);
+  if (n_items == 0) return {keys_sorted, items_sorted, seg_start, n_unique};
+  de::launch_build_keys(reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
+                        reinterpret_cast<const de::TableDesc*>(tables.data_ptr()),
+                        static_cast<int>(n_tables), static_cast<int>(n_inputs), batch, src_batch,
+                        to_peers(src_ptrs), ids64, keys.data_ptr<int64_t>(),
+                        reinterpret_cast<uint32_t*>(items.data_ptr<int>()), sm_count(), stream);
+  check_launch();
+  size_t sort_bytes = de::sort_pairs_temp_bytes(n_items);
+  size_t uniq_bytes = de::unique_temp_bytes(n_items);
+  Tensor temp = at::empty({static_cast<int64_t>(std::max(sort_bytes, uniq_bytes)) + 16},
+                          at::TensorOptions().device(descs.device()).dtype(at::kByte));
+  de::sort_pairs(temp.data_ptr(), sort_bytes, keys.data_ptr<int64_t>(),
+                 keys_sorted.data_ptr<int64_t>(),
+                 reinterpret_cast<const uint32_t*>(items.data_ptr<int>()),
+                 reinterpret_cast<uint32_t*>(items_sorted.data_ptr<int>()), n_items,
+                 bit_length(total_rows), stream);
+  de::unique_segments(temp.data_ptr(), uniq_bytes, keys_sorted.data_ptr<int64_t>(), n_items,
+                      seg_start.data_ptr<int64_t>(), n_unique.data_ptr<int64_t>(), stream);
+  check_launch();
+  return {keys_sorted, items_sorted, seg_start, n_unique};
+}
+
+void segment_update(const Tensor& descs, const Tensor& tables, int64_t n_tables, int64_t batch,
+                    int64_t grad_batch, int64_t grad_stride, at::IntArrayRef grad_ptrs,
+                    const Tensor& sorted_keys, const Tensor& sorted_items, const Tensor& seg_start,
+                    const Tensor& n_unique, int64_t opt_kind, double lr, double eps, double beta1,
+                    double beta2, double bias1, double bias2, double grad_scale,
+                    double weight_decay, int64_t lr_ptr, const c10::optional<Tensor>& emit_keys,
+                    const c10::optional<Tensor>& emit_rows, int64_t max_width, bool grad_bf16,
+                    bool vec4) {
+  c10::cuda::CUDAGuard guard(descs.device());
+  de::OptimizerArgs opt;
+  opt.kind = static_cast<int32_t>(opt_kind);
+  opt.lr = static_cast<float>(lr);
+  opt.eps = static_cast<float>(eps);
+  opt.beta1 = static_cast<float>(beta1);
+  opt.beta2 = static_cast<float>(beta2);
+  opt.bias1 = static_cast<float>(bias1);
+  opt.bias2 = static_cast<float>(bias2);
+  opt.grad_scale = static_cast<float>(grad_scale);
+  opt.weight_decay = static_cast<float>(weight_decay);
+  opt.lr_ptr = reinterpret_cast<const float*>(lr_ptr);
+  if (opt.kind == de::kOptEmit) TORCH_CHECK(emit_keys.has_value() && emit_rows.has_value());
+  de::launch_segment_update(
+      reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
+      reinterpret_cast<const de::TableDesc*>(tables.data_ptr()), static_cast<int>(n_tables), batch,
+      grad_batch, grad_stride, to_peers(grad_ptrs), sorted_keys.data_ptr<int64_t>(),
+      reinterpret_cast<const uint32_t*>(sorted_items.data_ptr<int>()),
+      seg_start.data_ptr<int64_t>(), n_unique.data_ptr<int64_t>(), sorted_keys.numel(), opt,
+      emit_keys.has_value() ? emit_keys->data_ptr<int64_t>() : nullptr,
+      emit_rows.has_value() ? emit_rows->data_ptr<float>() : nullptr, static_cast<int>(max_width),
+      grad_bf16, vec4, sm_count(), cur_stream());
+  check_launch();
+}
+
+// ------------------------------------------------------------------ single-table convenience
+// (used by the Embedding layer; builds a one-entry descriptor on the fly)
+Tensor upload_bytes(const void* host, size_t bytes, const at::Device& dev) {
+  Tensor t = at::empty({static_cast<int64_t>(bytes)},
+                       at::TensorOptions().device(dev).dtype(at::kByte));
+  DE_CUDA_CHECK(cudaMemcpyAsync(t.data_ptr(), host, bytes, cudaMemcpyHostToDevice, cur_stream()));
+  return t;
+}
+
+de::InputDesc single_desc(const void* table, const Tensor& values,
+                          const c10::optional<Tensor>& offsets, int64_t hotness, int64_t rows,
+                          int64_t width, int64_t combiner) {
+  de::InputDesc d;
+  std::memset(&d, 0, sizeof(d));
+  d.table = table;
+  d.ids = values.data_ptr();
+  d.offsets = offsets.has_value() ? offsets->data_ptr<int64_t>() : nullptr;
+  d.sub_rows = rows;
+  d.width = static_cast<int32_t>(width);
+  d.hotness = offsets.has_value() ? 0 : static_cast<int32_t>(hotness);
+  d.combiner = static_cast<int32_t>(combiner);
+  return d;
+}
+
+void check_ids(const Tensor& values, const c10::optional<Tensor>& offsets) {
+  TORCH_CHECK(values.is_cuda() && values.is_contiguous(), "ids must be a contiguous CUDA tensor");
+  TORCH_CHECK(values.scalar_type() == at::kInt || values.scalar_type() == at::kLong,
+              "ids must be int32 or int64");
+  if (offsets.has_value())
+    TORCH_CHECK(offsets->is_cuda() && offsets->scalar_type() == at::kLong &&
+                    offsets->is_contiguous(),
+                "row_splits must be a contiguous int64 CUDA tensor");
+}
+
+// out[b, :] = combine_{k in sample b} param[ids[k], :]
+Tensor embedding_lookup_fwd(const Tensor& param, const Tensor& values,
+                            const c10::optional<Tensor>& offsets, int64_t hotness, int64_t batch,
+                            int64_t combiner, bool out_bf16) {
+  TORCH_CHECK(param.is_cuda() && param.dim() == 2 && param.scalar_type() == at::kFloat &&
+                  param.is_contiguous(),
+              "param must be a contiguous fp32 [rows, width] CUDA tensor");
+  check_ids(values, offsets);
+  c10::cuda::CUDAGuard guard(param.device());
+  const int64_t width = param.size(1);
+  Tensor out = at::empty({batch, width},
+                         param.options().dtype(out_bf16 ? at::kBFloat16 : at::kFloat));
+  if (batch == 0) return out;
+  de::InputDesc d = single_desc(param.data_ptr(), values, offsets, hotness, param.size(0), width,
+                                combiner);
+  Tensor dd = upload_bytes(&d, sizeof(d), param.device());
+  de::PeerPtrs src, dst;
+  std::memset(&src, 0, sizeof(src));
+  std::memset(&dst, 0, sizeof(dst));
+  dst.p[0] = out.data_ptr();
+  de::launch_lookup_fwd(reinterpret_cast<const de::InputDesc*>(dd.data_ptr()), 1, batch, batch,
+                        batch, width, src, dst, 0, values.scalar_type() == at::kLong, out_bf16,
+                        width % 4 == 0, sm_count(), cur_stream());
+  check_launch();
+  return out;
+}
+
+// dst[ids[k], :] += scale * w * grad[sample(k), :]    (atomic; dst may be a dense grad buffer)
+void embedding_scatter_add(Tensor dst, const Tensor& values, const c10::optional<Tensor>& offsets,
+                           int64_t hotness, int64_t batch, int64_t combiner, const Tensor& grad,
+                           double scale) {
+  TORCH_CHECK(dst.is_cuda() && dst.dim() == 2 && dst.scalar_type() == at::kFloat &&
+              dst.is_contiguous());
+  TORCH_CHECK(grad.is_cuda() && grad.dim() == 2 && grad.stride(1) == 1);
+  check_ids(values, offsets);
+  if (batch == 0) return;
+  c10::cuda::CUDAGuard guard(dst.device());
+  const int64_t width = dst.size(1);
+  de::InputDesc d = single_desc(dst.data_ptr(), values, offsets, hotness, dst.size(0), width,
+                                combiner);
+  Tensor dd = upload_bytes(&d, sizeof(d), dst.device());
+  de::PeerPtrs src, gp;
+  std::memset(&src, 0, sizeof(src));
+  std::memset(&gp, 0, sizeof(gp));
+  gp.p[0] = grad.data_ptr();
+  const bool bf16 = grad.scalar_type() == at::kBFloat16;
+  TORCH_CHECK(bf16 || grad.scalar_type() == at::kFloat, "grad must be fp32 or bf16");
+  const int64_t gstride = grad.stride(0);
+  const bool vec4 = (width % 4 == 0) && (gstride % 4 == 0) &&
+                    (reinterpret_cast<uintptr_t>(grad.data_ptr()) % 16 == 0);
+  de::launch_scatter_add_bwd(reinterpret_cast<const de::InputDesc*>(dd.data_ptr()), 1, batch,
+                             batch, batch, gstride, src, gp, 0, static_cast<float>(scale), nullptr,
+                             values.scalar_type() == at::kLong, bf16, vec4, sm_count(),
+                             cur_stream());
+  check_launch();
+}
+
+// Deduplicated sparse gradient: (unique_ids sorted ascending, summed gradient rows)
+std::tuple<Tensor, Tensor> embedding_lookup_grad(const Tensor& values,
+                                                 const c10::optional<Tensor>& offsets,
+                                                 int64_t hotness, int64_t batch, int64_t combiner,
+                                                 const Tensor& grad, int64_t num_rows) {
+  TORCH_CHECK(grad.is_cuda() && grad.dim() == 2 && grad.stride(1) == 1);
+  check_ids(values, offsets);
+  c10::cuda::CUDAGuard guard(grad.device());
+  const int64_t width = grad.size(1);
+  const int64_t n_items = values.numel();
+  auto f32 = grad.options().dtype(at::kFloat);
+  auto i64 = grad.options().dtype(at::kLong);
+  if (n_items == 0) return {at::empty({0}, i64), at::empty({0, width}, f32)};
+  de::InputDesc d = single_desc(nullptr, values, offsets, hotness, num_rows, width, combiner);
+  de::TableDesc t;
+  std::memset(&t, 0, sizeof(t));
+  t.rows = num_rows;
+  t.width = static_cast<int32_t>(width);
+  Tensor dd = upload_bytes(&d, sizeof(d), grad.device());
+  Tensor td = upload_bytes(&t, sizeof(t), grad.device());
+  auto sorted = sort_items(dd, td, 1, 1, batch, batch, {}, values.scalar_type() == at::kLong,
+                           n_items, num_rows);
+  Tensor emit_keys = at::empty({n_items}, i64);
+  Tensor emit_rows = at::empty({n_items, width}, f32);
+  const bool bf16 = grad.scalar_type() == at::kBFloat16;
+  const int64_t gstride = grad.stride(0);
+  const bool vec4 = (width % 4 == 0) && (gstride % 4 == 0) &&
+                    (reinterpret_cast<uintptr_t>(grad.data_ptr()) % 16 == 0);
+  std::vector<int64_t> gp = {reinterpret_cast<int64_t>(grad.data_ptr())};
+  segment_update(dd, td, 1, batch, batch, gstride, gp, std::get<0>(sorted), std::get<1>(sorted),
+                 std::get<2>(sorted), std::get<3>(sorted), de::kOptEmit, 0, 0, 0, 0, 1, 1, 1.0, 0, 0,
+                 emit_keys, emit_rows, width, bf16, vec4);
+  // sizing the IndexedSlices-style result needs the unique count on the host (compat path only)
+  int64_t n_unique = std::get<3>(sorted).item<int64_t>();
+  if (n_unique > 0) {
+    // ids outside the table collapse into one trailing sentinel segment: drop it
+    int64_t last = emit_keys.narrow(0, n_unique - 1, 1).item<int64_t>();
+    if (last >= num_rows) --n_unique;
+  }
+  return {emit_keys.narrow(0, 0, n_unique), emit_rows.narrow(0, 0, n_unique)};
+}
+
+Tensor row_to_split(const Tensor& indices, int64_t num_rows) {
+  TORCH_CHECK(indices.is_cuda() && indices.dim() == 2 && indices.size(1) == 2 &&
+                  indices.scalar_type() == at::kLong && indices.is_contiguous(),
+              "indices must be a contiguous int64 [nnz, 2] CUDA tensor");
+  c10::cuda::CUDAGuard guard(indices.device());
+  Tensor splits = at::empty({num_rows + 1}, indices.options());
+  de::launch_row_to_split(indices.data_ptr<int64_t>(), indices.size(0), num_rows,
+                          splits.data_ptr<int64_t>(), cur_stream());
+  check_launch();
+  return splits;
+}
+
+void hash_init(Tensor table) {
+  TORCH_CHECK(table.is_cuda() && table.scalar_type() == at::kLong && table.is_contiguous());
+  c10::cuda::CUDAGuard guard(table.device());
+  de::launch_hash_init(table.data_ptr<int64_t>(), table.numel() / 2, cur_stream());
+  check_launch();
+}
+
+Tensor integer_lookup(Tensor table, Tensor count, Tensor next_index, const Tensor& keys,
+                      int64_t capacity) {
+  TORCH_CHECK(table.is_cuda() && count.is_cuda() && next_index.is_cuda() && keys.is_cuda());
+  TORCH_CHECK(table.scalar_type() == at::kLong && keys.scalar_type() == at::kLong &&
+              next_index.scalar_type() == at::kLong && count.scalar_type() == at::kInt);
+  c10::cuda::CUDAGuard guard(table.device());
+  Tensor k = keys.contiguous();
+  Tensor out = at::empty_like(k);
+  de::launch_integer_lookup(table.data_ptr<int64_t>(), table.numel() / 2,
+                            reinterpret_cast<uint32_t*>(count.data_ptr<int>()),
+                            next_index.data_ptr<int64_t>(), k.data_ptr<int64_t>(), k.numel(),
+                            capacity, out.data_ptr<int64_t>(), cur_stream());
+  check_launch();
+  return out;
+}
+
+// ------------------------------------------------------------------ communication ops
+void barrier(at::IntArrayRef flag_ptrs, Tensor epoch, int64_t rank, int64_t world, int64_t channel,
+             int64_t timeout_cycles, Tensor error_flag) {
+  c10::cuda::CUDAGuard guard(epoch.device());
+  de::launch_barrier(to_peers(flag_ptrs), reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()),
+                     static_cast<int>(rank), static_cast<int>(world), static_cast<int>(channel),
+                     static_cast<unsigned long long>(timeout_cycles), error_flag.data_ptr<int>(),
+                     cur_stream());
+  check_launch();
+}
+
+void allreduce(at::IntArrayRef buf_ptrs, at::IntArrayRef flag_ptrs, Tensor epoch, int64_t rank,
+               int64_t world, int64_t n_elems, double scale, bool bf16, int64_t channel,
+               int64_t timeout_cycles, Tensor error_flag, int64_t mc_ptr) {
+  c10::cuda::CUDAGuard guard(epoch.device());
+  if (mc_ptr != 0) {
+    de::launch_allreduce_multimem(reinterpret_cast<void*>(mc_ptr), to_peers(flag_ptrs),
+                                  reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()),
+                                  static_cast<int>(rank), static_cast<int>(world), n_elems,
+                                  static_cast<float>(scale), bf16, static_cast<int>(channel),
+                                  static_cast<unsigned long long>(timeout_cycles),
+                                  error_flag.data_ptr<int>(), sm_count(), cur_stream());
+  } else {
+    de::launch_allreduce(to_peers(buf_ptrs), to_peers(flag_ptrs),
+                         reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()),
+                         static_cast<int>(rank), static_cast<int>(world), n_elems,
+                         static_cast<float>(scale), bf16, static_cast<int>(channel),
+                         static_cast<unsigned long long>(timeout_cycles),
+                         error_flag.data_ptr<int>(), sm_count(), cur_stream());
+  }
+  check_launch();
+}
+
+void gather_segments(const Tensor& segs, at::IntArrayRef src_ptrs, Tensor dst,
+                     int64_t max_seg_elems) {
+  TORCH_CHECK(segs.is_cuda() && segs.scalar_type() == at::kLong && segs.is_contiguous());
+  TORCH_CHECK(dst.is_cuda() && dst.is_contiguous());
+  c10::cuda::CUDAGuard guard(dst.device());
+  de::launch_gather_segments(segs.data_ptr<int64_t>(), static_cast<int>(segs.size(0)),
+                             to_peers(src_ptrs), dst.data_ptr(),
+                             static_cast<int>(dst.element_size()), max_seg_elems, cur_stream());
+  check_launch();
+}
+
+void copy_cast_2d(const Tensor& src, int64_t dst_ptr, int64_t dst_stride, bool dst_bf16,
+                  double scale) {
+  TORCH_CHECK(src.is_cuda() && src.dim() == 2 && src.stride(1) == 1);
+  c10::cuda::CUDAGuard guard(src.device());
+  const bool src_bf16 = src.scalar_type() == at::kBFloat16;
+  TORCH_CHECK(src_bf16 || src.scalar_type() == at::kFloat);
+  de::launch_copy_cast_2d(src.data_ptr(), src.stride(0), reinterpret_cast<void*>(dst_ptr),
+                          dst_stride, src.size(0), src.size(1), src_bf16, dst_bf16,
+                          static_cast<float>(scale), cur_stream());
+  check_launch();
+}
+
+// ------------------------------------------------------------------ symmetric memory (IPC)
+// Buffers that peers map must not come from the caching allocator (its blocks are sub-ranges
+// of larger cudaMalloc segments), so they are cudaMalloc'd here and wrapped with from_blob.
+Tensor symm_alloc(int64_t nbytes, int64_t device_index) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device_index));
+  void* ptr = nullptr;
+  const size_t padded = (static_cast<size_t>(nbytes) + 255) & ~static_cast<size_t>(255);
+  DE_CUDA_CHECK(cudaMalloc(&ptr, padded));
+  DE_CUDA_CHECK(cudaMemset(ptr, 0, padded));
+  DE_CUDA_CHECK(cudaDeviceSynchronize());
+  auto deleter = [](void* p) { cudaFree(p); };
+  return at::from_blob(ptr, {static_cast<int64_t>(padded)}, deleter,
+                       at::TensorOptions()
+                           .device(at::Device(at::kCUDA, static_cast<c10::DeviceIndex>(device_index)))
+                           .dtype(at::kByte));
+}
+
+Tensor ipc_get_handle(const Tensor& buf) {
+  TORCH_CHECK(buf.is_cuda());
+  cudaIpcMemHandle_t h;
+  DE_CUDA_CHECK(cudaIpcGetMemHandle(&h, buf.data_ptr()));
+  Tensor out = at::empty({static_cast<int64_t>(sizeof(h))}, at::TensorOptions().dtype(at::kByte));
+  std::memcpy(out.data_ptr(), &h, sizeof(h));
+  return out;
+}
+
+int64_t ipc_open(const Tensor& handle, int64_t device_index) {
+  TORCH_CHECK(!handle.is_cuda() && handle.numel() == sizeof(cudaIpcMemHandle_t));
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device_index));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle.data_ptr(), sizeof(h));
+  void* ptr = nullptr;
+  DE_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return reinterpret_cast<int64_t>(ptr);
+}
+
+void ipc_close(int64_t ptr, int64_t device_index) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device_index));
+  cudaIpcCloseMemHandle(reinterpret_cast<void*>(ptr));
+}
+
+// Map a host tensor's storage for zero-copy GPU access (CPU-offloaded tables): returns the
+// device-visible pointer of pinned (cudaHostRegister'ed / pin_memory) memory.
+int64_t host_device_pointer(const Tensor& host) {
+  TORCH_CHECK(!host.is_cuda());
+  void* dptr = nullptr;
+  DE_CUDA_CHECK(cudaHostGetDevicePointer(&dptr, host.data_ptr(), 0));
+  return reinterpret_cast<int64_t>(dptr);
+}
+
+}  // namespace
+
+TORCH_LIBRARY(de_b200, m) {
+  m.def("struct_sizes() -> int[]", &struct_sizes);
+  m.def(
+      "lookup_fwd(Tensor descs, int n_inputs, int batch, int src_batch, int dst_batch, "
+      "int dst_stride, int[] src_ptrs, int[] dst_ptrs, int rot, bool ids64, bool out_bf16, "
+      "bool vec4) -> ()",
+      &lookup_fwd);
+  m.def(
+      "scatter_add_bwd(Tensor descs, int n_inputs, int batch, int src_batch, int grad_batch, "
+      "int grad_stride, int[] src_ptrs, int[] grad_ptrs, int rot, float scale, int scale_ptr, bool ids64, "
+      "bool grad_bf16, bool vec4) -> ()",
+      &scatter_add_bwd);
+  m.def(
+      "sort_items(Tensor descs, Tensor tables, int n_tables, int n_inputs, int batch, "
+      "int src_batch, int[] src_ptrs, bool ids64, int n_items, int total_rows) -> "
+      "(Tensor, Tensor, Tensor, Tensor)",
+      &sort_items);
+  m.def(
+      "segment_update(Tensor descs, Tensor tables, int n_tables, int batch, int grad_batch, "
+      "int grad_stride, int[] grad_ptrs, Tensor sorted_keys, Tensor sorted_items, "
+      "Tensor seg_start, Tensor n_unique, int opt_kind, float lr, float eps, float beta1, "
+      "float beta2, float bias1, float bias2, float grad_scale, float weight_decay, int lr_ptr, "
+      "Tensor? emit_keys, Tensor? emit_rows, int max_width, bool grad_bf16, bool vec4) -> ()",
+      &segment_update);
+  m.def(
+      "embedding_lookup_fwd(Tensor param, Tensor values, Tensor? offsets, int hotness, int batch, "
+      "int combiner, bool out_bf16) -> Tensor",
+      &embedding_lookup_fwd);
+  m.def(
+      "embedding_scatter_add(Tensor(a!) dst, Tensor values, Tensor? offsets, int hotness, "
+      "int batch, int combiner, Tensor grad, float scale) -> ()",
+      &embedding_scatter_add);
+  m.def(
+      "embedding_lookup_grad(Tensor values, Tensor? offsets, int hotness, int batch, int combiner, "
+      "Tensor grad, int num_rows) -> (Tensor, Tensor)",
+      &embedding_lookup_grad);
+  m.def("row_to_split(Tensor indices, int num_rows) -> Tensor", &row_to_split);
+  m.def("hash_init(Tensor(a!) table) -> ()", &hash_init);
+  m.def(
+      "integer_lookup(Tensor(a!) table, Tensor(b!) count, Tensor(c!) next_index, Tensor keys, "
+      "int capacity) -> Tensor",
+      &integer_lookup);
+  m.def(
+      "barrier(int[] flag_ptrs, Tensor(a!) epoch, int rank, int world, int channel, "
+      "int timeout_cycles, Tensor(b!) error_flag) -> ()",
+      &barrier);
+  m.def(
+      "allreduce(int[] buf_ptrs, int[] flag_ptrs, Tensor(a!) epoch, int rank, int world, "
+      "int n_elems, float scale, bool bf16, int channel, int timeout_cycles, "
+      "Tensor(b!) error_flag, int mc_ptr) -> ()",
+      &allreduce);
+  m.def("gather_segments(Tensor segs, int[] src_ptrs, Tensor(a!) dst, int max_seg_elems) -> ()",
+        &gather_segments);
+  m.def("copy_cast_2d(Tensor src, int dst_ptr, int dst_stride, bool dst_bf16, float scale) -> ()",
+        &copy_cast_2d);
+  m.def("symm_alloc(int nbytes, int device_index) -> Tensor", &symm_alloc);
+  m.def("ipc_get_handle(Tensor buf) -> Tensor", &ipc_get_handle);
+  m.def("ipc_open(Tensor handle, int device_index) -> int", &ipc_open);
+  m.def("ipc_close(int ptr, int device_index) -> ()", &ipc_close);
+  m.def("host_device_pointer(Tensor host) -> int", &host_device_pointer);
+}

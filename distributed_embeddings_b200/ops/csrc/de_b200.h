@@ -1,0 +1,126 @@
+// Host-callable launchers of the sm_100a kernels. Plain C++ (no torch headers) so that the .cu
+// files compile in seconds; bindings.cpp adapts these to TORCH_LIBRARY ops.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace de {
+
+constexpr int kMaxPeers = 16;
+
+// One entry per local input (feature) served by this rank. Resolved once from the sharding plan
+// so a single persistent kernel handles every table of the rank (hundreds in the large models).
+struct alignas(16) InputDesc {
+  const void* table;       // base of the (fused) local table, row major [rows, width] fp32
+  const void* ids;         // direct ids pointer, or nullptr -> src_ptrs[s] + ids_off
+  const int64_t* offsets;  // CSR row_splits for ragged inputs, nullptr for fixed hotness
+  int64_t ids_off;         // element offset of this input inside a source staging buffer
+  int64_t id_shift;        // added to the raw id (row slices: -first_row)
+  int64_t sub_rows;        // ids valid after the shift: [0, sub_rows); others contribute zero
+  int64_t row_base;        // first row of this sub-table inside the fused table
+  int32_t width;           // embedding width (columns)
+  int32_t hotness;         // ids per sample for fixed hotness, 0 = ragged (use offsets)
+  int32_t dst_col;         // first column in the destination (requester output / grad) row
+  int32_t combiner;        // 0 = sum, 1 = mean
+  int32_t local_table;     // index into the rank's TableDesc array
+  int32_t pad0;
+  int64_t item_off;        // first (key, item) slot of this input in the sorted-update arrays
+};
+
+struct PeerPtrs {
+  void* p[kMaxPeers];
+};
+
+enum OptimizerKind : int32_t { kOptSGD = 0, kOptAdagrad = 1, kOptRowwiseAdagrad = 2, kOptAdam = 3, kOptEmit = 4 };
+
+// One entry per (fused) local table, used by the sorted/deduplicated update path.
+struct alignas(16) TableDesc {
+  void* weight;       // [rows, width] fp32
+  void* state0;       // Adagrad accumulator [rows,width] / row-wise [rows] / Adam m
+  void* state1;       // Adam v
+  int64_t rows;
+  int64_t key_base;   // first global row key of this table (prefix sum of rows)
+  int32_t width;
+  int32_t pad;
+};
+
+struct OptimizerArgs {
+  int32_t kind;
+  float lr;
+  float eps;
+  float beta1, beta2;
+  float bias1, bias2;  // Adam bias corrections 1-beta^t
+  float grad_scale;    // applied to the summed gradient (1/world for the global-mean contract)
+  float weight_decay;
+  const float* lr_ptr;  // optional device-resident learning rate (overrides lr; graph replay safe)
+};
+
+// ---- pooled lookup forward (+ optional fused push to peer output buffers) ------------------
+// ids come from src.p[g / src_batch] (peer mapped) or desc.ids; pooled rows are stored to
+// dst.p[g / dst_batch] + (g % dst_batch) * dst_stride + dst_col.
+void launch_lookup_fwd(const InputDesc* descs, int n_inputs, int64_t batch, int64_t src_batch,
+                       int64_t dst_batch, int64_t dst_stride, const PeerPtrs& src,
+                       const PeerPtrs& dst, int rot, bool ids64, bool out_bf16, bool vec4,
+                       int sm_count, cudaStream_t stream);
+
+// ---- backward: atomic scatter-add of (scaled) gradient rows into the table (SGD fast path,
+// also used to build dense gradients of replicated tables). Gradient rows are pulled from
+// grad.p[g / grad_batch] + (g % grad_batch) * grad_stride + dst_col (peer mapped).
+void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch, int64_t src_batch,
+                            int64_t grad_batch, int64_t grad_stride, const PeerPtrs& src,
+                            const PeerPtrs& grad, int rot, float scale, const float* scale_ptr,
+                            bool ids64, bool grad_bf16, bool vec4, int sm_count,
+                            cudaStream_t stream);
+
+// ---- backward: sorted / deduplicated path -----------------------------------------------
+void launch_build_keys(const InputDesc* descs, const TableDesc* tables, int n_tables, int n_inputs,
+                       int64_t batch, int64_t src_batch, const PeerPtrs& src, bool ids64, int64_t* keys,
+                       uint32_t* items, int sm_count, cudaStream_t stream);
+size_t sort_pairs_temp_bytes(int64_t n);
+void sort_pairs(void* temp, size_t temp_bytes, const int64_t* keys_in, int64_t* keys_out,
+                const uint32_t* items_in, uint32_t* items_out, int64_t n, int end_bit,
+                cudaStream_t stream);
+size_t unique_temp_bytes(int64_t n);
+// seg_start[u] = first sorted position of unique key u; *n_unique on device; seg_start[n_unique] = n
+void unique_segments(void* temp, size_t temp_bytes, const int64_t* sorted_keys, int64_t n,
+                     int64_t* seg_start, int64_t* n_unique, cudaStream_t stream);
+void launch_segment_update(const InputDesc* descs, const TableDesc* tables, int n_tables,
+                           int64_t batch, int64_t grad_batch, int64_t grad_stride,
+                           const PeerPtrs& grad, const int64_t* sorted_keys,
+                           const uint32_t* sorted_items, const int64_t* seg_start,
+                           const int64_t* n_unique, int64_t n_items, const OptimizerArgs& opt,
+                           int64_t* emit_keys, float* emit_rows, int max_width, bool grad_bf16,
+                           bool vec4, int sm_count, cudaStream_t stream);
+
+// ---- misc ---------------------------------------------------------------------------------
+void launch_row_to_split(const int64_t* coo_indices, int64_t nnz, int64_t num_rows,
+                         int64_t* row_splits, cudaStream_t stream);
+void launch_hash_init(int64_t* table, int64_t n_slots, cudaStream_t stream);
+void launch_integer_lookup(int64_t* table, int64_t n_slots, uint32_t* counts, int64_t* next_index,
+                           const int64_t* keys, int64_t n, int64_t capacity, int64_t* out,
+                           cudaStream_t stream);
+
+// ---- communication kernels ----------------------------------------------------------------
+// Flag barrier over peer-mapped signal pads: flags.p[r] points at rank r's pad (>= world slots
+// of uint32 per channel); epoch lives in device memory so the kernel can be graph-replayed.
+void launch_barrier(const PeerPtrs& flags, uint32_t* epoch, int rank, int world, int channel,
+                    unsigned long long timeout_cycles, int* error_flag, cudaStream_t stream);
+// Two-shot all-reduce (reduce-scatter + all-gather) over peer-mapped buffers, fused with scale.
+void launch_allreduce(const PeerPtrs& bufs, const PeerPtrs& flags, uint32_t* epoch, int rank,
+                      int world, int64_t n_elems, float scale, bool bf16, int channel,
+                      unsigned long long timeout_cycles, int* error_flag, int sm_count,
+                      cudaStream_t stream);
+// Multimem (NVLS) variant: mc_ptr is the multicast mapping of the same symmetric buffer.
+void launch_allreduce_multimem(void* mc_ptr, const PeerPtrs& flags, uint32_t* epoch, int rank,
+                               int world, int64_t n_elems, float scale, bool bf16, int channel,
+                               unsigned long long timeout_cycles, int* error_flag, int sm_count,
+                               cudaStream_t stream);
+// Segmented P2P pull: segs[j] = {src_rank, src_elem_off, dst_elem_off, n_elems}
+void launch_gather_segments(const int64_t* segs, int n_seg, const PeerPtrs& src, void* dst,
+                            int elem_bytes, int64_t max_seg_elems, cudaStream_t stream);
+// Copy/cast a strided 2-D block into a (symmetric) buffer: dst[r, c] = cast(src[r, c])
+void launch_copy_cast_2d(const void* src, int64_t src_stride, void* dst, int64_t dst_stride,
+                         int64_t rows, int64_t cols, bool src_bf16, bool dst_bf16, float scale,
+                         cudaStream_t stream);
+
+}  // namespace de

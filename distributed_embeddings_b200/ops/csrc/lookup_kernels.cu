@@ -1,0 +1,322 @@
+// Pooled embedding lookup forward and atomic scatter-add backward for sm_100a.
+//
+// One persistent, descriptor-driven kernel serves every table of the rank.  A warp owns a tile
+// of 32 consecutive samples of one input; inside the warp, LPR lanes cooperate on one row
+// (LPR * VEC columns per pass) and 32/LPR rows are in flight side by side, with a further 4x
+// unroll so that >= 4 independent 16-byte row loads per lane are outstanding (HBM3e needs ~45 KB
+// in flight per SM).  Sources of ids and destinations of pooled rows are *peer-mapped* pointers:
+// with world_size > 1 the kernel reads indices straight out of the requesters' staging buffers
+// and stores pooled rows straight into the requesters' output tensors over NVLink (the two
+// all-to-alls of the reference, dist_model_parallel.py:211 and :872, fused into the lookup).
+// Tile order interleaves destination ranks (rotated by the local rank) so all NVLink egress and
+// every peer's ingress stay evenly loaded instead of all GPUs bursting at peer 0.
+//
+// Capability parity: EmbeddingLookUpVariableHot / ...HotWide (reference
+// cc/kernels/embedding_lookup_kernels.cu:175-336) + the dense tf.gather/reduce path.
+#include "common.cuh"
+
+namespace de {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarpsPerBlock = kThreads / 32;
+constexpr int kTile = 32;  // samples per warp tile
+constexpr int kUnroll = 4;
+
+struct TileCoord {
+  int f;        // local input
+  int d;        // destination (requester) rank
+  int64_t g0;   // first global sample
+  int nsamp;    // samples in tile
+};
+
+__device__ __forceinline__ TileCoord decode_tile(int64_t t, int n_inputs, int n_dst,
+                                                 int64_t tiles_per_dst, int64_t batch,
+                                                 int64_t dst_batch, int rot) {
+  TileCoord c;
+  int dd = static_cast<int>(t % n_dst);
+  int64_t rest = t / n_dst;
+  c.f = static_cast<int>(rest % n_inputs);
+  int64_t chunk = rest / n_inputs;
+  c.d = (dd + rot) % n_dst;
+  int64_t local0 = chunk * kTile;
+  c.g0 = static_cast<int64_t>(c.d) * dst_batch + local0;
+  int64_t lim = min(dst_batch, batch - static_cast<int64_t>(c.d) * dst_batch);
+  int64_t rem = lim - local0;
+  c.nsamp = rem < kTile ? static_cast<int>(rem < 0 ? 0 : rem) : kTile;
+  return c;
+}
+
+template <typename IdT>
+struct IdReader {
+  const IdT* direct;      // per-input direct pointer (global batch order) or nullptr
+  const int64_t* offsets; // CSR
+  const PeerPtrs* src;
+  int64_t ids_off;
+  int64_t src_batch;
+  int hot;
+
+  // number of ids of sample g and the pointer to its first id
+  __device__ __forceinline__ const IdT* sample(int64_t g, int& n) const {
+    if (offsets != nullptr) {
+      int64_t a = offsets[g], b = offsets[g + 1];
+      n = static_cast<int>(b - a);
+      return direct + a;
+    }
+    n = hot;
+    if (direct != nullptr) return direct + g * hot;
+    int64_t s = g / src_batch;
+    int64_t i = g - s * src_batch;
+    return reinterpret_cast<const IdT*>(src->p[s]) + ids_off + i * hot;
+  }
+};
+
+template <typename IdT>
+__device__ __forceinline__ IdReader<IdT> make_reader(const InputDesc& D, const PeerPtrs& src,
+                                                     int64_t src_batch) {
+  IdReader<IdT> r;
+  r.direct = reinterpret_cast<const IdT*>(D.ids);
+  r.offsets = D.offsets;
+  r.src = &src;
+  r.ids_off = D.ids_off;
+  r.src_batch = src_batch;
+  r.hot = D.hotness;
+  return r;
+}
+
+// =============================================================================== forward
+template <typename IdT, typename OutT, int VEC>
+__global__ void __launch_bounds__(kThreads)
+lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
+                  int64_t src_batch, int64_t dst_batch, int64_t dst_stride,
+                  const __grid_constant__ PeerPtrs src, const __grid_constant__ PeerPtrs dst,
+                  int rot) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
+  const int n_dst = static_cast<int>((batch + dst_batch - 1) / dst_batch);
+  const int64_t tiles_per_dst = (dst_batch + kTile - 1) / kTile;
+  const int64_t total = static_cast<int64_t>(n_inputs) * n_dst * tiles_per_dst;
+
+  for (int64_t t = warp; t < total; t += n_warps) {
+    const TileCoord tc = decode_tile(t, n_inputs, n_dst, tiles_per_dst, batch, dst_batch, rot);
+    if (tc.nsamp <= 0) continue;
+    const InputDesc D = descs[tc.f];
+    const int W = D.width;
+    const int nvec = (W + VEC - 1) / VEC;           // VEC==4 requires W % 4 == 0
+    const int lpr = min(32, pow2_ceil(nvec));       // lanes per row
+    const int rpw = 32 / lpr;                       // rows in flight per warp
+    const int sub = lane / lpr, li = lane - sub * lpr;
+    const float* table = reinterpret_cast<const float*>(D.table);
+    OutT* out_base = reinterpret_cast<OutT*>(dst.p[tc.d]);
+    const int64_t i0 = tc.g0 - static_cast<int64_t>(tc.d) * dst_batch;
+    const IdReader<IdT> rd = make_reader<IdT>(D, src, src_batch);
+    const bool onehot = (D.hotness == 1) && (D.offsets == nullptr);
+
+    for (int c0 = 0; c0 < nvec; c0 += lpr) {        // column pass (one pass when W <= 128)
+      const int cv = c0 + li;
+      const bool col_ok = cv < nvec;
+      const int col = cv * VEC;
+      if (onehot) {
+        // 4 samples per lane group in flight
+        for (int r0 = 0; r0 < tc.nsamp; r0 += rpw * kUnroll) {
+          FVec<VEC> acc[kUnroll];
+          bool ok[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const int r = r0 + u * rpw + sub;
+            ok[u] = (r < tc.nsamp) && col_ok;
+            acc[u].zero();
+            if (ok[u]) {
+              int n;
+              const IdT* p = rd.sample(tc.g0 + r, n);
+              const int64_t id = static_cast<int64_t>(*p) + D.id_shift;
+              if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows))
+                acc[u] = ld_f32<VEC>(table + (D.row_base + id) * W + col);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            if (ok[u]) {
+              const int r = r0 + u * rpw + sub;
+              st_act<OutT, VEC>(out_base + (i0 + r) * dst_stride + D.dst_col + col, acc[u]);
+            }
+          }
+        }
+      } else {
+        for (int r0 = 0; r0 < tc.nsamp; r0 += rpw) {
+          const int r = r0 + sub;
+          if (r >= tc.nsamp || !col_ok) continue;
+          int n;
+          const IdT* p = rd.sample(tc.g0 + r, n);
+          FVec<VEC> acc;
+          acc.zero();
+          int h = 0;
+          for (; h + kUnroll <= n; h += kUnroll) {
+            int64_t id[kUnroll];
+            FVec<VEC> x[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) id[u] = static_cast<int64_t>(p[h + u]) + D.id_shift;
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+              x[u].zero();
+              if (static_cast<uint64_t>(id[u]) < static_cast<uint64_t>(D.sub_rows))
+                x[u] = ld_f32<VEC>(table + (D.row_base + id[u]) * W + col);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) acc.add(x[u]);
+          }
+          for (; h < n; ++h) {
+            const int64_t id = static_cast<int64_t>(p[h]) + D.id_shift;
+            if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows))
+              acc.add(ld_f32<VEC>(table + (D.row_base + id) * W + col));
+          }
+          if (D.combiner == 1 && n > 0) acc.scale(1.0f / static_cast<float>(n));
+          st_act<OutT, VEC>(out_base + (i0 + r) * dst_stride + D.dst_col + col, acc);
+        }
+      }
+    }
+  }
+}
+
+// =============================================================================== backward
+// dst_table[row] += scale * w_sample * grad_row   (vector RED, no return value)
+template <typename IdT, typename GradT, int VEC>
+__global__ void __launch_bounds__(kThreads)
+scatter_add_bwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
+                       int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
+                       const __grid_constant__ PeerPtrs src, const __grid_constant__ PeerPtrs grad,
+                       int rot, float scale, const float* __restrict__ scale_ptr) {
+  if (scale_ptr != nullptr) scale *= *scale_ptr;  // device-resident lr (CUDA-graph friendly)
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
+  const int n_dst = static_cast<int>((batch + grad_batch - 1) / grad_batch);
+  const int64_t tiles_per_dst = (grad_batch + kTile - 1) / kTile;
+  const int64_t total = static_cast<int64_t>(n_inputs) * n_dst * tiles_per_dst;
+
+  for (int64_t t = warp; t < total; t += n_warps) {
+    const TileCoord tc = decode_tile(t, n_inputs, n_dst, tiles_per_dst, batch, grad_batch, rot);
+    if (tc.nsamp <= 0) continue;
+    const InputDesc D = descs[tc.f];
+    const int W = D.width;
+    const int nvec = (W + VEC - 1) / VEC;
+    const int lpr = min(32, pow2_ceil(nvec));
+    const int rpw = 32 / lpr;
+    const int sub = lane / lpr, li = lane - sub * lpr;
+    float* table = reinterpret_cast<float*>(const_cast<void*>(D.table));
+    const GradT* grad_base = reinterpret_cast<const GradT*>(grad.p[tc.d]);
+    const int64_t i0 = tc.g0 - static_cast<int64_t>(tc.d) * grad_batch;
+    const IdReader<IdT> rd = make_reader<IdT>(D, src, src_batch);
+
+    for (int c0 = 0; c0 < nvec; c0 += lpr) {
+      const int cv = c0 + li;
+      const bool col_ok = cv < nvec;
+      const int col = cv * VEC;
+      for (int r0 = 0; r0 < tc.nsamp; r0 += rpw * kUnroll) {
+        FVec<VEC> g[kUnroll];
+        const IdT* p[kUnroll];
+        int n[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int r = r0 + u * rpw + sub;
+          n[u] = 0;
+          p[u] = nullptr;
+          if (r < tc.nsamp && col_ok) {
+            p[u] = rd.sample(tc.g0 + r, n[u]);
+            g[u] = ld_act<GradT, VEC>(grad_base + (i0 + r) * grad_stride + D.dst_col + col);
+            float w = scale;
+            if (D.combiner == 1 && n[u] > 0) w /= static_cast<float>(n[u]);
+            g[u].scale(w);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          for (int h = 0; h < n[u]; ++h) {
+            const int64_t id = static_cast<int64_t>(p[u][h]) + D.id_shift;
+            if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows))
+              red_add_f32<VEC>(table + (D.row_base + id) * W + col, g[u]);
+          }
+        }
+      }
+    }
+  }
+}
+
+int grid_for(int64_t total_tiles, int sm_count, int blocks_per_sm) {
+  int64_t blocks = (total_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  int64_t cap = static_cast<int64_t>(sm_count) * blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+int64_t count_tiles(int n_inputs, int64_t batch, int64_t dst_batch) {
+  int64_t n_dst = (batch + dst_batch - 1) / dst_batch;
+  int64_t tiles_per_dst = (dst_batch + kTile - 1) / kTile;
+  return static_cast<int64_t>(n_inputs) * n_dst * tiles_per_dst;
+}
+
+}  // namespace
+
+#define DE_DISPATCH_FWD(IdT, OutT, VEC)                                                        \
+  lookup_fwd_kernel<IdT, OutT, VEC><<<grid, kThreads, 0, stream>>>(                            \
+      descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src, dst, rot)
+
+void launch_lookup_fwd(const InputDesc* descs, int n_inputs, int64_t batch, int64_t src_batch,
+                       int64_t dst_batch, int64_t dst_stride, const PeerPtrs& src,
+                       const PeerPtrs& dst, int rot, bool ids64, bool out_bf16, bool vec4,
+                       int sm_count, cudaStream_t stream) {
+  if (n_inputs <= 0 || batch <= 0) return;
+  const int grid = grid_for(count_tiles(n_inputs, batch, dst_batch), sm_count, 8);
+  if (vec4) {
+    if (ids64) {
+      if (out_bf16) DE_DISPATCH_FWD(int64_t, __nv_bfloat16, 4);
+      else DE_DISPATCH_FWD(int64_t, float, 4);
+    } else {
+      if (out_bf16) DE_DISPATCH_FWD(int32_t, __nv_bfloat16, 4);
+      else DE_DISPATCH_FWD(int32_t, float, 4);
+    }
+  } else {
+    if (ids64) {
+      if (out_bf16) DE_DISPATCH_FWD(int64_t, __nv_bfloat16, 1);
+      else DE_DISPATCH_FWD(int64_t, float, 1);
+    } else {
+      if (out_bf16) DE_DISPATCH_FWD(int32_t, __nv_bfloat16, 1);
+      else DE_DISPATCH_FWD(int32_t, float, 1);
+    }
+  }
+}
+
+#define DE_DISPATCH_BWD(IdT, GradT, VEC)                                                       \
+  scatter_add_bwd_kernel<IdT, GradT, VEC><<<grid, kThreads, 0, stream>>>(                      \
+      descs, n_inputs, batch, src_batch, grad_batch, grad_stride, src, grad, rot, scale, scale_ptr)
+
+void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch, int64_t src_batch,
+                            int64_t grad_batch, int64_t grad_stride, const PeerPtrs& src,
+                            const PeerPtrs& grad, int rot, float scale, const float* scale_ptr,
+                            bool ids64, bool grad_bf16, bool vec4, int sm_count,
+                            cudaStream_t stream) {
+  if (n_inputs <= 0 || batch <= 0) return;
+  const int grid = grid_for(count_tiles(n_inputs, batch, grad_batch), sm_count, 8);
+  if (vec4) {
+    if (ids64) {
+      if (grad_bf16) DE_DISPATCH_BWD(int64_t, __nv_bfloat16, 4);
+      else DE_DISPATCH_BWD(int64_t, float, 4);
+    } else {
+      if (grad_bf16) DE_DISPATCH_BWD(int32_t, __nv_bfloat16, 4);
+      else DE_DISPATCH_BWD(int32_t, float, 4);
+    }
+  } else {
+    if (ids64) {
+      if (grad_bf16) DE_DISPATCH_BWD(int64_t, __nv_bfloat16, 1);
+      else DE_DISPATCH_BWD(int64_t, float, 1);
+    } else {
+      if (grad_bf16) DE_DISPATCH_BWD(int32_t, __nv_bfloat16, 1);
+      else DE_DISPATCH_BWD(int32_t, float, 1);
+    }
+  }
+}
+
+}  // namespace de

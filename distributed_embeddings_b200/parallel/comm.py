@@ -1,0 +1,187 @@
+"""Communication runtime: one process per GPU, ``torch.distributed`` for bootstrap and cold
+paths, peer-mapped *symmetric buffers* (cudaMalloc + CUDA IPC) for the hot paths.
+
+Every rank allocates the same set of buffers; handles are exchanged once through the process
+group and opened with ``cudaIpcOpenMemHandle`` so each rank holds a device pointer to every
+peer's copy.  Kernels then load/store peer HBM directly over NVLink 5 / NVSwitch.  Cross-rank
+ordering uses a signal pad of per-(channel, writer) epoch words written with ``st.release.sys``
+and polled with ``ld.acquire.sys`` under a bounded-spin watchdog (no infinite device spins).
+
+Replaces the Horovod layer of the reference (dist_model_parallel.py:22-24).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops import _native
+
+# ~2 s at 2 GHz before a flag wait gives up and raises the error flag
+DEFAULT_TIMEOUT_CYCLES = int(os.environ.get("DE_B200_FLAG_TIMEOUT_CYCLES", str(4_000_000_000)))
+NUM_CHANNELS = 16
+
+
+def dist_ready() -> bool:
+  return dist.is_available() and dist.is_initialized()
+
+
+class SymmetricBuffer:
+  """A same-sized device buffer on every rank, with peer pointers to all copies."""
+
+  def __init__(self, ctx: "CommContext", nbytes: int, name: str = ""):
+    self.ctx = ctx
+    self.name = name
+    self.nbytes = int(nbytes)
+    dev = ctx.device
+    ops = _native.require()
+    self.local = ops.symm_alloc(self.nbytes, dev.index)  # uint8 tensor, zero filled
+    self.ptrs: List[int] = [0] * ctx.world_size
+    self._opened: List[int] = []
+    self.ptrs[ctx.rank] = self.local.data_ptr()
+    if ctx.world_size > 1:
+      handle = ops.ipc_get_handle(self.local)
+      gathered: List[Optional[torch.Tensor]] = [None] * ctx.world_size
+      dist.all_gather_object(gathered, handle.numpy().tobytes(), group=ctx.group)
+      for r, raw in enumerate(gathered):
+        if r == ctx.rank:
+          continue
+        h = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        p = ops.ipc_open(h, dev.index)
+        self.ptrs[r] = p
+        self._opened.append(p)
+
+  def view(self, dtype: torch.dtype, shape, byte_offset: int = 0) -> torch.Tensor:
+    """Typed view of the local copy."""
+    n = 1
+    for s in shape:
+      n *= int(s)
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    assert byte_offset + nbytes <= self.local.numel(), (self.name, byte_offset, nbytes,
+                                                         self.local.numel())
+    return self.local[byte_offset:byte_offset + nbytes].view(dtype).view(*shape)
+
+  def peer_ptrs(self, byte_offset: int = 0) -> List[int]:
+    return [p + byte_offset for p in self.ptrs]
+
+  def close(self):
+    if self._opened:
+      ops = _native.require()
+      for p in self._opened:
+        ops.ipc_close(p, self.ctx.device.index)
+      self._opened = []
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+
+class CommContext:
+  """Rank / world bookkeeping plus the device-side synchronisation state of one process group."""
+
+  _default: Optional["CommContext"] = None
+
+  def __init__(self, group=None, device: Optional[torch.device] = None):
+    if dist_ready():
+      self.group = group
+      self.rank = dist.get_rank(group)
+      self.world_size = dist.get_world_size(group)
+    else:
+      self.group = None
+      self.rank, self.world_size = 0, 1
+    if device is None:
+      if torch.cuda.is_available():
+        device = torch.device("cuda", torch.cuda.current_device())
+      else:
+        device = torch.device("cpu")
+    self.device = torch.device(device)
+    self.is_cuda = self.device.type == "cuda"
+    self.p2p = False
+    self.signal: Optional[SymmetricBuffer] = None
+    self._epochs: Dict[int, torch.Tensor] = {}
+    self.error_flag: Optional[torch.Tensor] = None
+    self.timeout_cycles = DEFAULT_TIMEOUT_CYCLES
+    if self.is_cuda and _native.available():
+      if self.world_size > _native.MAX_PEERS:
+        raise ValueError(f"at most {_native.MAX_PEERS} ranks per P2P domain are supported")
+      self._init_p2p()
+
+  # -- construction helpers ---------------------------------------------------------------
+  @classmethod
+  def default(cls, device=None) -> "CommContext":
+    if cls._default is None or (device is not None and
+                                torch.device(device) != cls._default.device) or (
+                                    cls._default.world_size != (dist.get_world_size()
+                                                                if dist_ready() else 1)):
+      cls._default = CommContext(device=device)
+    return cls._default
+
+  def _init_p2p(self):
+    with torch.cuda.device(self.device):
+      self.signal = SymmetricBuffer(self, NUM_CHANNELS * _native.MAX_PEERS * 4, "signal_pad")
+      self.error_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+      if self.world_size > 1:
+        dist.barrier(group=self.group)
+      self.p2p = True
+
+  def epoch(self, channel: int) -> torch.Tensor:
+    """Device-resident epoch words of a channel ([0] epoch, [1] block counter): kernels bump them
+    on the device so a captured CUDA graph can be replayed without host patching."""
+    if channel not in self._epochs:
+      self._epochs[channel] = torch.zeros(2, dtype=torch.int32, device=self.device)
+    return self._epochs[channel]
+
+  # -- collectives --------------------------------------------------------------------------
+  def alloc(self, nbytes: int, name: str = "") -> SymmetricBuffer:
+    if not self.p2p:
+      raise RuntimeError("symmetric buffers need CUDA + the native extension")
+    with torch.cuda.device(self.device):
+      return SymmetricBuffer(self, nbytes, name)
+
+  def barrier(self, channel: int = 0):
+    """Device-side barrier on the current stream (no host synchronisation)."""
+    if self.world_size == 1:
+      return
+    if not self.p2p:
+      dist.barrier(group=self.group)
+      return
+    _native.ops().barrier(self.signal.ptrs, self.epoch(channel), self.rank, self.world_size,
+                          channel, self.timeout_cycles, self.error_flag)
+
+  def allreduce_(self, buf: SymmetricBuffer, n_elems: int, dtype: torch.dtype, scale: float = 1.0,
+                 channel: int = 15, byte_offset: int = 0, mc_ptr: int = 0):
+    """In-place sum (x scale) over all ranks of a symmetric buffer; one kernel, no NCCL."""
+    if self.world_size == 1:
+      if scale != 1.0:
+        buf.view(dtype, (n_elems,), byte_offset).mul_(scale)
+      return
+    _native.ops().allreduce(buf.peer_ptrs(byte_offset), self.signal.ptrs, self.epoch(channel),
+                            self.rank, self.world_size, n_elems, float(scale),
+                            dtype == torch.bfloat16, channel, self.timeout_cycles, self.error_flag,
+                            mc_ptr)
+
+  def check_errors(self):
+    """Host check of the watchdog flag (synchronises; call outside hot loops)."""
+    if self.error_flag is not None:
+      v = int(self.error_flag.item())
+      if v != 0:
+        raise RuntimeError(
+            f"rank {self.rank}: peer flag wait timed out waiting for rank {v - 1} - a rank is "
+            "hung, crashed, or running a mismatched plan")
+
+  # -- cold-path helpers (torch.distributed) ------------------------------------------------
+  def all_gather_object(self, obj):
+    if self.world_size == 1:
+      return [obj]
+    out = [None] * self.world_size
+    dist.all_gather_object(out, obj, group=self.group)
+    return out
+
+  def broadcast_(self, tensor: torch.Tensor, src: int = 0):
+    if self.world_size > 1:
+      dist.broadcast(tensor, src=src, group=self.group)
+    return tensor
