@@ -1,0 +1,404 @@
+"""Multi-rank test cases, launched by ``tests/dist_utils.launch`` (one process per rank).
+
+Mirrors the strategy matrix of the reference's ``dist_model_parallel_test.py`` (run_and_test
+:244-291 and the test_* cases :319-640): the oracle is an undistributed model holding the full
+tables whose gradients are averaged over ranks; the distributed model is loaded with the same
+weights through ``set_weights`` and must match after one SGD step.
+"""
+import random
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import nn
+
+import distributed_embeddings_b200 as de
+from distributed_embeddings_b200 import dist_model_parallel as dmp
+from distributed_embeddings_b200.ops.ragged import RaggedIds
+
+
+class CustomEmbedding(nn.Module):
+  """User-defined layer: only get_config / from_config + a 2-D parameter are required."""
+
+  def __init__(self, input_dim, output_dim):
+    super().__init__()
+    self.input_dim, self.output_dim = input_dim, output_dim
+    self.params = nn.Parameter(torch.rand(input_dim, output_dim))
+
+  def forward(self, ids):
+    return nn.functional.embedding(ids.to(torch.int64), self.params)
+
+  def get_config(self):
+    return {"input_dim": self.input_dim, "output_dim": self.output_dim}
+
+  @classmethod
+  def from_config(cls, cfg):
+    return cls(cfg["input_dim"], cfg["output_dim"])
+
+
+class EmbeddingListModel(nn.Module):
+
+  def __init__(self, table_sizes, distribute=False, strategy="basic", dp_input=True,
+               input_table_map=None, column_slice_threshold=None, test_custom_layer=False,
+               combiner=None, row_slice_threshold=None, data_parallel_threshold=None,
+               gpu_embedding_size=None, device="cpu", backend="auto", compute_dtype=None):
+    super().__init__()
+    embs = []
+    for rows, width in table_sizes:
+      if test_custom_layer:
+        embs.append(CustomEmbedding(rows, width))
+      else:
+        embs.append(de.Embedding(rows, width, combiner=combiner, device=device))
+    self.input_table_map = input_table_map
+    if distribute:
+      self.dist_embeddings = de.DistributedEmbedding(
+          embs, strategy=strategy, dp_input=dp_input, input_table_map=input_table_map,
+          column_slice_threshold=column_slice_threshold, row_slice_threshold=row_slice_threshold,
+          data_parallel_threshold=data_parallel_threshold, gpu_embedding_size=gpu_embedding_size,
+          device=device, backend=backend, compute_dtype=compute_dtype)
+      self.embeddings = None
+    else:
+      self.dist_embeddings = None
+      self.embeddings = nn.ModuleList(embs).to(device)
+    imap = input_table_map or list(range(len(table_sizes)))
+    total = sum(table_sizes[t][1] for t in imap)
+    self.dense = nn.Linear(total, 5).to(device)
+
+  def forward(self, inputs):
+    if self.dist_embeddings is not None:
+      outs = self.dist_embeddings(inputs)
+    else:
+      imap = self.input_table_map or list(range(len(self.embeddings)))
+      outs = [self.embeddings[t](i) for i, t in zip(inputs, imap)]
+    outs = [o.float() for o in outs]
+    return self.dense(torch.cat(outs, dim=1))
+
+
+def gen_table_sizes(seed, num_tables=None, world=1):
+  rng = random.Random(seed)
+  if num_tables is None:
+    num_tables = rng.randint(1, 2 * world)
+  return [[rng.randint(4, 20), rng.randint(4, 15)] for _ in range(num_tables)]
+
+
+def gen_input_to_table_map(seed, num_tables):
+  rng = random.Random(seed + 1)
+  mapping = list(range(num_tables))
+  for _ in range(3):
+    mapping.append(rng.randint(0, num_tables - 1))
+  rng.shuffle(mapping)
+  return mapping
+
+
+def gen_inputs(seed, global_batch, table_sizes, input_to_table_map=None, hotness=None,
+               ragged=False, device="cpu", dtype=torch.int64):
+  """Global inputs, identical on every rank (seeded)."""
+  g = torch.Generator().manual_seed(seed + 7)
+  imap = input_to_table_map or list(range(len(table_sizes)))
+  if hotness is not None and isinstance(hotness, int):
+    hotness = [hotness] * len(imap)
+  outs = []
+  for j, t in enumerate(imap):
+    rows = table_sizes[t][0]
+    if hotness is None:
+      outs.append(torch.randint(0, rows, (global_batch,), generator=g, dtype=dtype).to(device))
+    elif ragged:
+      lens = torch.randint(1, hotness[j] + 1, (global_batch,), generator=g)
+      vals = torch.randint(0, rows, (int(lens.sum()),), generator=g, dtype=dtype)
+      outs.append(RaggedIds.from_row_lengths(vals, lens).to(device))
+    else:
+      outs.append(
+          torch.randint(0, rows, (global_batch, hotness[j]), generator=g, dtype=dtype).to(device))
+  return outs
+
+
+def slice_batch(x, rank, local_batch):
+  if isinstance(x, RaggedIds):
+    return x.slice_rows(rank * local_batch, (rank + 1) * local_batch)
+  return x[rank * local_batch:(rank + 1) * local_batch]
+
+
+def run_and_test(ref_model, ref_inputs, test_model, test_inputs, fwd_tol=None, bwd_tol=1e-5,
+                 lr=1.5):
+  world = dist.get_world_size() if dist.is_initialized() else 1
+  # same dense + embedding weights everywhere
+  for p in ref_model.parameters():
+    if world > 1:
+      dist.broadcast(p.data, src=0)
+  ref_tables = [e.embeddings if hasattr(e, "embeddings") else e.params
+                for e in ref_model.embeddings]
+  test_model.dist_embeddings.set_weights([t.detach().cpu().numpy() for t in ref_tables])
+  with torch.no_grad():
+    test_model.dense.weight.copy_(ref_model.dense.weight)
+    test_model.dense.bias.copy_(ref_model.dense.bias)
+
+  ref_params = list(ref_model.parameters())
+  ref_out = torch.cumsum(ref_model(ref_inputs), dim=1)
+  ref_grads = torch.autograd.grad(ref_out.sum(), ref_params)
+  ref_grads = [g.to_dense() if g.is_sparse else g for g in ref_grads]
+  if world > 1:
+    for g in ref_grads:
+      dist.all_reduce(g)
+      g /= world
+
+  test_params = list(test_model.parameters())
+  test_out = torch.cumsum(test_model(test_inputs), dim=1)
+  tape = dmp.DistributedGradientTape()
+  test_grads = tape.gradient(test_out.sum(), test_params)
+
+  if fwd_tol is None:
+    assert torch.equal(ref_out, test_out), (ref_out - test_out).abs().max()
+  else:
+    torch.testing.assert_close(ref_out, test_out, rtol=fwd_tol, atol=fwd_tol)
+
+  with torch.no_grad():
+    for p, g in zip(ref_params, ref_grads):
+      p -= lr * g
+    for p, g in zip(test_params, test_grads):
+      if g is None:
+        continue
+      p -= lr * (g.to_dense() if g.is_sparse else g)
+
+  test_weights = test_model.dist_embeddings.get_weights(all_ranks=True)
+  for ref_w, test_w in zip(ref_tables, test_weights):
+    torch.testing.assert_close(ref_w.detach().cpu(), torch.from_numpy(test_w), rtol=bwd_tol,
+                               atol=bwd_tol)
+  torch.testing.assert_close(ref_model.dense.weight, test_model.dense.weight, rtol=bwd_tol,
+                             atol=bwd_tol)
+
+
+def _generic_case(rank, world, device, backend, *, seed=0, table_sizes=None, num_tables=None,
+                  strategy="basic", dp_input=True, shared=False, hotness=None, ragged=False,
+                  combiner=None, global_batch=24, fwd_tol=None, bwd_tol=1e-5, id_dtype=torch.int64,
+                  **kw):
+  torch.manual_seed(seed)
+  if table_sizes is None:
+    table_sizes = gen_table_sizes(seed, num_tables, world)
+  imap = gen_input_to_table_map(seed, len(table_sizes)) if shared else None
+  if hotness is not None and combiner is None:
+    combiner = "sum"
+  ref = EmbeddingListModel(table_sizes, distribute=False, input_table_map=imap, combiner=combiner,
+                           test_custom_layer=kw.get("test_custom_layer", False), device=device)
+  test = EmbeddingListModel(table_sizes, distribute=True, strategy=strategy, dp_input=dp_input,
+                            input_table_map=imap, combiner=combiner, device=device,
+                            backend=backend, **kw)
+  glob = gen_inputs(seed, global_batch, table_sizes, imap, hotness, ragged, device, id_dtype)
+  local_batch = global_batch // world
+  dp_inputs = [slice_batch(x, rank, local_batch) for x in glob]
+  if dp_input:
+    test_inputs = dp_inputs
+  else:
+    ids = test.dist_embeddings.strategy.input_ids_list[rank]
+    test_inputs = [glob[i] for i in ids]
+  run_and_test(ref, dp_inputs, test, test_inputs, fwd_tol, bwd_tol)
+  return test
+
+
+def case_basic(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=11, **kw)
+
+
+def case_memory_balanced(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=12, strategy="memory_balanced",
+                num_tables=2 * world + 1, **kw)
+
+
+def case_memory_optimized(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=13, strategy="memory_optimized",
+                num_tables=2 * world + 1, **kw)
+
+
+def case_row_slice(rank, world, device, backend, **kw):
+  sizes = gen_table_sizes(14, 2 * world, world)
+  _generic_case(rank, world, device, backend, seed=14, table_sizes=sizes,
+                row_slice_threshold=8 * 13, **kw)
+
+
+def case_data_parallel(rank, world, device, backend, **kw):
+  sizes = gen_table_sizes(15, 2 * world + 1, world)
+  _generic_case(rank, world, device, backend, seed=15, table_sizes=sizes,
+                data_parallel_threshold=8 * 9, **kw)
+
+
+def case_shared_dp(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=16, num_tables=world + 2, shared=True, **kw)
+
+
+def case_shared_mp(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=17, num_tables=world + 2, shared=True,
+                dp_input=False, **kw)
+
+
+def case_mp_input(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=18, num_tables=2 * world, dp_input=False, **kw)
+
+
+def case_column_slice_merge(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=19,
+                table_sizes=[[100, 8], [5, 8], [10, 8], [25, 4]], strategy="memory_balanced",
+                column_slice_threshold=45, **kw)
+
+
+def case_column_slice_threshold(rank, world, device, backend, **kw):
+  sizes = gen_table_sizes(20, world + 1, world)
+  _generic_case(rank, world, device, backend, seed=20, table_sizes=sizes,
+                column_slice_threshold=30, **kw)
+
+
+def case_column_slice_dup_worker(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=21,
+                table_sizes=[[10, 4], [11, 2], [4, 2], [4, 2]], strategy="memory_balanced",
+                column_slice_threshold=10, **kw)
+
+
+def case_fewer_tables_than_workers(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=22, table_sizes=[[16, 12]], **kw)
+
+
+def case_custom_layer(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=23, num_tables=2 * world,
+                test_custom_layer=True, **kw)
+
+
+def case_all_modes(rank, world, device, backend, **kw):
+  sizes = [[2, 8], [2, 16], [10, 8], [10, 16], [10, 16], [10, 32], [10, 128], [100, 16], [100, 32],
+           [100, 128], [1000, 16], [1000, 48], [1000, 128], [10000, 64], [5000, 8], [50000, 8]]
+  _generic_case(rank, world, device, backend, seed=24, table_sizes=sizes,
+                strategy="memory_balanced", data_parallel_threshold=1000,
+                column_slice_threshold=100000, row_slice_threshold=400000, **kw)
+
+
+def case_multihot_dp(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=25, num_tables=2 * world, hotness=5,
+                fwd_tol=1e-6, **kw)
+
+
+def case_multihot_mp(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=26, num_tables=2 * world, hotness=5,
+                dp_input=False, fwd_tol=1e-6, **kw)
+
+
+def case_multihot_mean(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=27, num_tables=2 * world, hotness=4,
+                combiner="mean", fwd_tol=1e-6, **kw)
+
+
+def case_ragged_dp(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=28, num_tables=2 * world, hotness=6,
+                ragged=True, fwd_tol=1e-6, **kw)
+
+
+def case_cpu_offload(rank, world, device, backend, **kw):
+  sizes = 4 * [[100, 32]] + 4 * [[1000, 64]]
+  test = _generic_case(rank, world, device, backend, seed=29, table_sizes=sizes, hotness=3,
+                       gpu_embedding_size=32000, fwd_tol=1e-6, **kw)
+  assert any(l.cpu_offloaded for l in test.dist_embeddings.local_embedding_layers)
+
+
+def case_int32_ids(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=30, num_tables=2 * world,
+                id_dtype=torch.int32, **kw)
+
+
+def case_dp_to_mp_input(rank, world, device, backend, **kw):
+  """Index exchange alone: every rank must receive the original global feature."""
+  n_feat = 2 * world + 1
+  rng = random.Random(5)
+  owners = [rng.randrange(world) for _ in range(n_feat)]
+  owners[0] = 0
+  rank_to_features = {r: [k for k in range(n_feat) if owners[k] == r] for r in range(world)}
+  if kw.get("unbalanced"):
+    rank_to_features = {r: (list(range(n_feat)) if r == 0 else []) for r in range(world)}
+  gb = 4 * world
+  sizes = [[50, 4]] * n_feat
+  glob = gen_inputs(3, gb, sizes, hotness=3, ragged=False, device=device)
+  glob_r = gen_inputs(4, gb, sizes, hotness=4, ragged=True, device=device)
+  mixed = [glob[k] if k % 2 == 0 else glob_r[k] for k in range(n_feat)]
+  local = [slice_batch(x, rank, gb // world) for x in mixed]
+  got = dmp.dp_to_mp_input(local, rank_to_features, rank, world)
+  assert list(got.keys()) == rank_to_features[rank]
+  for k, v in got.items():
+    if isinstance(mixed[k], RaggedIds):
+      assert v.to_lists() == mixed[k].to_lists()
+    else:
+      assert torch.equal(v.to(mixed[k].dtype), mixed[k])
+
+
+def case_broadcast(rank, world, device, backend, **kw):
+  torch.manual_seed(100 + rank)
+  sizes = [[11, 7], [5, 8], [3, 8], [5, 8], [12, 25], [3, 12], [7, 13]]
+  model = EmbeddingListModel(sizes, distribute=True, strategy="basic", device=device,
+                             backend=backend)
+  emb_w = [np.random.RandomState(1).rand(r, w).astype(np.float32) for r, w in sizes]
+  model.dist_embeddings.set_weights(emb_w)
+  ids = [torch.randint(0, s[0], (3,), generator=torch.Generator().manual_seed(2)).to(device)
+         for s in sizes]
+  out = model(ids)
+  outs = [torch.empty_like(out) for _ in range(world)]
+  dist.all_gather(outs, out.detach())
+  if world > 1:
+    assert not torch.allclose(outs[0], outs[1])
+  dmp.broadcast_variables(model, root_rank=0)
+  out = model(ids)
+  dist.all_gather(outs, out.detach())
+  for o in outs[1:]:
+    assert torch.equal(outs[0], o)
+
+
+def case_errors(rank, world, device, backend, **kw):
+  import pytest
+  sizes = [[10, 4], [10, 4], [10, 4]]
+  model = EmbeddingListModel(sizes, distribute=True, device=device, backend=backend)
+  with pytest.raises(ValueError):
+    model.dist_embeddings.set_weights([np.zeros((10, 4), np.float32)])
+  with pytest.raises(ValueError):
+    model.dist_embeddings([torch.zeros(4, dtype=torch.int64, device=device)])
+  mp_model = EmbeddingListModel(sizes, distribute=True, dp_input=False, device=device,
+                                backend=backend)
+  n_local = len(mp_model.dist_embeddings.strategy.local_maps[rank])
+  if world > 1:
+    with pytest.raises(ValueError, match="not divisible"):
+      mp_model.dist_embeddings(
+          [torch.zeros(world + 1, dtype=torch.int64, device=device)] * n_local)
+  with pytest.raises(ValueError):
+    de.DistributedEmbedding([de.Embedding(4, 4)], strategy="bogus", device=device)
+
+
+def case_hybrid_optimizer(rank, world, device, backend, **kw):
+  """DistributedOptimizer path (the reference's model.fit flow): loss + weights must match a
+  manual all-reduce step."""
+  torch.manual_seed(40)
+  sizes = gen_table_sizes(40, 2 * world, world)
+  ref = EmbeddingListModel(sizes, distribute=False, device=device)
+  test = EmbeddingListModel(sizes, distribute=True, strategy="memory_balanced", device=device,
+                            backend=backend)
+  for p in ref.parameters():
+    dist.broadcast(p.data, src=0)
+  tables = [e.embeddings for e in ref.embeddings]
+  test.dist_embeddings.set_weights([t.detach().cpu().numpy() for t in tables])
+  torch.manual_seed(41 + rank)
+  with torch.no_grad():
+    test.dense.weight.normal_()  # deliberately different per rank before the broadcast
+  dmp.BroadcastGlobalVariablesCallback(0)(test)
+  with torch.no_grad():
+    ref.dense.weight.copy_(test.dense.weight)
+    ref.dense.bias.copy_(test.dense.bias)
+  glob = gen_inputs(40, 8 * world, sizes, device=device)
+  inputs = [slice_batch(x, rank, 8) for x in glob]
+  opt = dmp.DistributedOptimizer(torch.optim.SGD(test.parameters(), lr=0.5))
+  opt.zero_grad()
+  loss = test(inputs).square().mean()
+  loss.backward()
+  opt.step()
+  ref_loss = ref(inputs).square().mean()
+  grads = torch.autograd.grad(ref_loss, list(ref.parameters()))
+  with torch.no_grad():
+    for p, g in zip(ref.parameters(), grads):
+      g = g.to_dense() if g.is_sparse else g
+      dist.all_reduce(g)
+      p -= 0.5 * g / world
+  torch.testing.assert_close(loss, ref_loss)
+  got = test.dist_embeddings.get_weights(all_ranks=True)
+  for t, w in zip(tables, got):
+    torch.testing.assert_close(t.detach().cpu(), torch.from_numpy(w), rtol=1e-5, atol=1e-5)
+  torch.testing.assert_close(ref.dense.weight, test.dense.weight, rtol=1e-5, atol=1e-5)

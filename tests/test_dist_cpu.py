@@ -1,0 +1,33 @@
+"""Multi-rank behaviour of DistributedEmbedding on CPU (gloo, torch back end).  The same cases
+run on GPUs with the fused back end in test_dist_gpu.py."""
+import pytest
+
+from dist_utils import launch
+
+CASES = [
+    "case_basic", "case_memory_balanced", "case_memory_optimized", "case_row_slice",
+    "case_data_parallel", "case_shared_dp", "case_shared_mp", "case_mp_input",
+    "case_column_slice_threshold", "case_fewer_tables_than_workers", "case_custom_layer",
+    "case_multihot_dp", "case_multihot_mp", "case_multihot_mean", "case_ragged_dp",
+    "case_cpu_offload", "case_int32_ids", "case_dp_to_mp_input", "case_broadcast", "case_errors",
+    "case_hybrid_optimizer",
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_world2(case):
+  launch(case, world=2)
+
+
+@pytest.mark.parametrize("case", ["case_column_slice_merge", "case_column_slice_dup_worker",
+                                  "case_all_modes", "case_basic", "case_row_slice"])
+def test_world4(case):
+  launch(case, world=4)
+
+
+def test_world3_uneven():
+  launch("case_memory_optimized", world=3, global_batch=24)
+
+
+def test_dp_to_mp_unbalanced():
+  launch("case_dp_to_mp_input", world=2, unbalanced=True)
