@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Headline benchmark: DLRM (MLPerf Criteo-1TB configuration) training throughput.
+
+``python bench.py --gpus N --steps K --warmup W`` (under torchrun for N > 1) runs K timed hybrid
+parallel training steps (forward, loss, backward with the fused embedding update, dense gradient
+all-reduce, dense SGD) at global batch 65536 and prints ONE JSON line from rank 0.
+
+* ``value``: global samples/s, device timed (CUDA events), max over ranks.
+* ``e2e``: the same metric through the public API with the per-step host->device copy of the
+  inputs from pinned memory and the device->host read of the loss inside the timed region.
+* ``--impl reference`` reports the unmodified reference (TensorFlow + Horovod) if importable.
+
+Reference counterpart: examples/dlrm/main.py + examples/benchmarks/synthetic_models/main.py
+(host wall-clock timing, :132-158); BASELINE.md for the published 8xA100 numbers.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BASELINE_SAMPLES_PER_SEC = 10416232.0  # 8xA100 AMP, reference examples/dlrm/README.md:8
+
+
+def parse_args():
+  p = argparse.ArgumentParser()
+  p.add_argument("--gpus", type=int, default=1)
+  p.add_argument("--steps", type=int, default=50)
+  p.add_argument("--warmup", type=int, default=10)
+  p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  p.add_argument("--global-batch", type=int, default=65536)
+  p.add_argument("--model", default="dlrm-mlperf",
+                 help="dlrm-mlperf | dlrm-small (26x100000) | dlrm-tiny (26x1000)")
+  p.add_argument("--backend", default="fused", choices=["fused", "torch"])
+  p.add_argument("--optimizer", default="sgd")
+  p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+  p.add_argument("--lr", type=float, default=24.0)
+  p.add_argument("--data-batches", type=int, default=4)
+  p.add_argument("--no-e2e", action="store_true")
+  p.add_argument("--column-slice-threshold", type=int, default=None)
+  p.add_argument("--cuda-graph", type=int, default=1)
+  return p.parse_args()
+
+
+def reference_arm(args):
+  """Run the unmodified reference through its own API - only possible when TensorFlow and
+  Horovod exist; this image has neither (no network), so report unavailability."""
+  sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+  why = None
+  try:
+    import tensorflow  # noqa: F401  pylint: disable=unused-import,import-outside-toplevel
+    import horovod.tensorflow  # noqa: F401  pylint: disable=unused-import,import-outside-toplevel
+    import distributed_embeddings  # noqa: F401  pylint: disable=unused-import,import-outside-toplevel
+  except Exception as e:  # pylint: disable=broad-except
+    why = f"{type(e).__name__}: {e}"
+  if why is None:
+    why = "reference imported but its custom op library (_embedding_lookup_ops.so) is not built"
+  rank = int(os.environ.get("RANK", "0"))
+  if rank == 0:
+    print(json.dumps({"impl": "reference",
+                      "unavailable": "reference needs TensorFlow+Horovod (not in image, no "
+                                     "network); python package installs to baseline/_ref but "
+                                     f"cannot import: {why}"[:300]}))
+  return 0
+
+
+class ClockSampler:
+  """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+  FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+            "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index: int):
+    self.gpu = gpu_index
+    self.path = tempfile.mktemp(suffix=".csv")
+    self.proc = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms",
+           "100", "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+    except Exception:  # pylint: disable=broad-except
+      self.proc = None
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:  # pylint: disable=broad-except
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    try:
+      for line in open(self.path):
+        f = [x.strip() for x in line.split(",")]
+        if len(f) < 9:
+          continue
+        try:
+          sm.append(float(f[1]))
+          mx.append(float(f[2]))
+        except ValueError:
+          continue
+        for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                              "sw_power_cap"), f[5:9]):
+          if val.lower().startswith("active"):
+            reasons.add(name)
+    except Exception:  # pylint: disable=broad-except
+      pass
+    finally:
+      try:
+        os.remove(self.path)
+      except OSError:
+        pass
+    sm.sort()
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def table_sizes_for(model: str):
+  from distributed_embeddings_b200.models.dlrm import mlperf_table_sizes
+  if model == "dlrm-mlperf":
+    return mlperf_table_sizes()
+  if model == "dlrm-small":
+    return 26 * [100000]
+  if model == "dlrm-tiny":
+    return 26 * [1000]
+  raise ValueError(model)
+
+
+def main():
+  args = parse_args()
+  if args.impl == "reference":
+    return reference_arm(args)
+
+  import torch
+  import torch.distributed as dist
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if world != args.gpus and world > 1:
+    args.gpus = world
+  torch.cuda.set_device(local_rank)
+  device = torch.device("cuda", local_rank)
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=device)
+
+  from distributed_embeddings_b200.models.dlrm import DLRM
+  from distributed_embeddings_b200.models.trainer import HybridTrainer
+  from distributed_embeddings_b200.ops import _native
+
+  torch.manual_seed(1234)  # same dense init on every rank (then broadcast anyway)
+  sizes = table_sizes_for(args.model)
+  compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+  gb = args.global_batch
+  assert gb % world == 0
+  lb = gb // world
+  model = DLRM(sizes, device=device, compute_dtype=compute_dtype, backend=args.backend,
+               column_slice_threshold=args.column_slice_threshold)
+  from distributed_embeddings_b200 import broadcast_variables
+  broadcast_variables(model)
+  trainer = HybridTrainer(model, lr=args.lr, embedding_optimizer=args.optimizer)
+
+  # ---- synthetic Criteo-shaped data in pinned host memory (uniform ids, random-init tables)
+  n_feat = len(sizes)
+  g = torch.Generator().manual_seed(99 + rank)
+  pool = []
+  for _ in range(args.data_batches):
+    num = torch.rand(lb, 13, generator=g).pin_memory()
+    cat = torch.stack([torch.randint(0, s, (lb,), generator=g, dtype=torch.int32)
+                       for s in sizes]).pin_memory()  # [26, lb] feature major = staging layout
+    lab = torch.randint(0, 2, (lb, 1), generator=g).float().pin_memory()
+    pool.append((num, cat, lab))
+  h2d_bytes = sum(t.numel() * t.element_size() for t in pool[0])
+
+  fused = args.backend == "fused"
+  engine = None
+  if fused:
+    from distributed_embeddings_b200.parallel.fused import FusedEngine
+    model.embedding._engine = FusedEngine(model.embedding)
+    engine = model.embedding._engine
+    engine.prepare(lb, [1] * n_feat, ids64=False)
+    cat_stage = engine.in_flat[:n_feat * lb].view(n_feat, lb)
+  num_d = torch.empty(lb, 13, device=device)
+  lab_d = torch.empty(lb, 1, device=device)
+  dev_pool = [(n.to(device), c.to(device), l.to(device)) for n, c, l in pool]
+
+  def step_from_device(i):
+    n, c, l = dev_pool[i % len(dev_pool)]
+    if fused:
+      cat_stage.copy_(c)
+      return trainer.step(n, None, l, staged=True)
+    return trainer.step(n, list(c.unbind(0)), l)
+
+  def step_e2e(i):
+    n, c, l = pool[i % len(pool)]
+    num_d.copy_(n, non_blocking=True)
+    lab_d.copy_(l, non_blocking=True)
+    if fused:
+      cat_stage.copy_(c, non_blocking=True)
+      loss = trainer.step(num_d, None, lab_d, staged=True)
+    else:
+      cd = c.to(device, non_blocking=True)
+      loss = trainer.step(num_d, list(cd.unbind(0)), lab_d)
+    return float(loss.item())  # device -> host read of the step result
+
+  def sync_all():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    sync_all()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(steps):
+      fn(i)
+    end.record()
+    sync_all()
+    ms = torch.tensor([start.elapsed_time(end)], device=device)
+    if world > 1:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+  for i in range(max(3, args.warmup)):
+    step_from_device(i)
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  _native.reset_launch_count()
+  total_ms = timed(step_from_device, args.steps)
+  launches = _native.launch_count()
+  clocks = sampler.stop() if rank == 0 else None
+
+  e2e = None
+  if not args.no_e2e:
+    for i in range(3):
+      step_e2e(i)
+    e2e_ms = timed(step_e2e, args.steps)
+    e2e = {"value": gb * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
+           "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d_bytes * world,
+           "d2h_bytes_per_step": 4 * world}
+  if engine is not None:
+    engine.ctx.check_errors()
+
+  if rank == 0:
+    ms_per_step = total_ms / args.steps
+    value = gb / (ms_per_step / 1e3)
+    table_gb = sum(sizes) * 128 * 4 / 2**30
+    out = {
+        "metric": "DLRM global samples/sec (device-timed, max over ranks)",
+        "value": value,
+        "unit": "samples/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": value / BASELINE_SAMPLES_PER_SEC,
+        "dtype": args.dtype,
+        "data": "synthetic (uniform Criteo-shaped ids, random-init tables)",
+        "impl": "b200",
+        "config": {
+            "model": f"DLRM {args.model}: 26 tables dim 128 ({sum(sizes)} rows, "
+                     f"{table_gb:.1f} GiB fp32), bottom 512-256-128, top 1024-1024-512-256-1",
+            "global_batch": gb,
+            "seq_len": 1,
+            "parallelism": f"hybrid: dp{world} dense + table-parallel embeddings "
+                           f"(memory_balanced), backend={args.backend}",
+            "optimizer": f"{args.optimizer} lr={args.lr} (embedding update fused in backward)",
+            "l2_policy": "inputs larger than L2: random rows of "
+                         f"{table_gb / world:.1f} GiB tables per GPU vs 126 MB L2",
+        },
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": launches,
+    }
+    print(json.dumps(out))
+  if world > 1:
+    dist.destroy_process_group()
+  return 0
+
+
+if __name__ == "__main__":
+  sys.exit(main())

@@ -28,7 +28,7 @@ INPUT_DESC = np.dtype([
     ("dst_col", "<i4"),
     ("combiner", "<i4"),
     ("local_table", "<i4"),
-    ("pad0", "<i4"),
+    ("flags", "<i4"),
     ("item_off", "<i8"),
     ("pad1", "<i8"),
 ])
@@ -79,13 +79,60 @@ def available() -> bool:
   return load(required=False)
 
 
+# number of kernels each native op launches (for the benchmark's launch accounting)
+_KERNELS_PER_OP = {
+    "lookup_fwd": 1, "scatter_add_bwd": 1, "sort_items": 12, "segment_update": 1,
+    "embedding_lookup_fwd": 1, "embedding_scatter_add": 1, "embedding_lookup_grad": 14,
+    "row_to_split": 1, "hash_init": 1, "integer_lookup": 1, "barrier": 1, "allreduce": 1,
+    "gather_segments": 1, "copy_cast_2d": 1, "dense_sgd": 1,
+}
+_launches = 0
+
+
+class _OpsProxy:
+  """Forwards to ``torch.ops.de_b200`` and counts kernel launches."""
+
+  def __init__(self, ns):
+    self._ns = ns
+    self._cache = {}
+
+  def __getattr__(self, name):
+    fn = self._cache.get(name)
+    if fn is None:
+      raw = getattr(self._ns, name)
+      k = _KERNELS_PER_OP.get(name, 0)
+
+      def fn(*args, __raw=raw, __k=k, **kwargs):
+        global _launches
+        _launches += __k
+        return __raw(*args, **kwargs)
+
+      self._cache[name] = fn
+    return fn
+
+
+_proxy = None
+
+
+def reset_launch_count():
+  global _launches
+  _launches = 0
+
+
+def launch_count() -> int:
+  return _launches
+
+
 def require():
   """Fail loudly when a CUDA tensor reaches an op but the extension is missing."""
+  global _proxy
   if not load(required=False):
     raise RuntimeError(
         "distributed_embeddings_b200: the native sm_100a extension is required for CUDA tensors "
         f"but could not be loaded ({_error!r}). There is no eager fallback on GPU.")
-  return torch.ops.de_b200
+  if _proxy is None:
+    _proxy = _OpsProxy(torch.ops.de_b200)
+  return _proxy
 
 
 def ops():

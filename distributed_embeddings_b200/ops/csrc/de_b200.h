@@ -23,7 +23,7 @@ struct alignas(16) InputDesc {
   int32_t dst_col;         // first column in the destination (requester output / grad) row
   int32_t combiner;        // 0 = sum, 1 = mean
   int32_t local_table;     // index into the rank's TableDesc array
-  int32_t pad0;
+  int32_t flags;           // bit 0: skip the store when the sample has no id inside this shard
   int64_t item_off;        // first (key, item) slot of this input in the sorted-update arrays
 };
 

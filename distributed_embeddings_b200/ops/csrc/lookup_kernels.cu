@@ -113,6 +113,7 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
     const int64_t i0 = tc.g0 - static_cast<int64_t>(tc.d) * dst_batch;
     const IdReader<IdT> rd = make_reader<IdT>(D, src, src_batch);
     const bool onehot = (D.hotness == 1) && (D.offsets == nullptr);
+    const bool skip_empty = (D.flags & 1) != 0;  // row slices: only the owner of an id writes
 
     for (int c0 = 0; c0 < nvec; c0 += lpr) {        // column pass (one pass when W <= 128)
       const int cv = c0 + li;
@@ -134,6 +135,8 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
               const int64_t id = static_cast<int64_t>(*p) + D.id_shift;
               if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows))
                 acc[u] = ld_f32<VEC>(table + (D.row_base + id) * W + col);
+              else if (skip_empty)
+                ok[u] = false;
             }
           }
 #pragma unroll
@@ -152,7 +155,7 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
           const IdT* p = rd.sample(tc.g0 + r, n);
           FVec<VEC> acc;
           acc.zero();
-          int h = 0;
+          int h = 0, hits = 0;
           for (; h + kUnroll <= n; h += kUnroll) {
             int64_t id[kUnroll];
             FVec<VEC> x[kUnroll];
@@ -161,17 +164,22 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
               x[u].zero();
-              if (static_cast<uint64_t>(id[u]) < static_cast<uint64_t>(D.sub_rows))
+              if (static_cast<uint64_t>(id[u]) < static_cast<uint64_t>(D.sub_rows)) {
                 x[u] = ld_f32<VEC>(table + (D.row_base + id[u]) * W + col);
+                ++hits;
+              }
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) acc.add(x[u]);
           }
           for (; h < n; ++h) {
             const int64_t id = static_cast<int64_t>(p[h]) + D.id_shift;
-            if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows))
+            if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows)) {
               acc.add(ld_f32<VEC>(table + (D.row_base + id) * W + col));
+              ++hits;
+            }
           }
+          if (skip_empty && hits == 0) continue;
           if (D.combiner == 1 && n > 0) acc.scale(1.0f / static_cast<float>(n));
           st_act<OutT, VEC>(out_base + (i0 + r) * dst_stride + D.dst_col + col, acc);
         }

@@ -14,6 +14,8 @@ from typing import Optional, Tuple, Union
 
 import torch
 
+torch.sparse.check_sparse_tensor_invariants.disable()
+
 from . import _native
 from .ragged import RaggedIds, SparseIds
 

@@ -1,0 +1,55 @@
+"""GPU runs of the distributed cases: fused back end (sm_100a kernels + P2P) and the torch/NCCL
+back end.  world=1 exercises the kernels on one GPU; world>=2 needs several GPUs (NVLink P2P)."""
+import pytest
+import torch
+
+from dist_utils import launch
+
+FUSED_CASES = [
+    "case_basic", "case_memory_balanced", "case_memory_optimized", "case_shared_dp",
+    "case_shared_mp", "case_mp_input", "case_column_slice_threshold",
+    "case_fewer_tables_than_workers", "case_multihot_dp", "case_multihot_mp", "case_multihot_mean",
+    "case_int32_ids", "case_errors", "case_hybrid_optimizer", "case_row_slice",
+    "case_data_parallel", "case_all_modes",
+]
+TORCH_CASES = ["case_basic", "case_ragged_dp", "case_custom_layer", "case_cpu_offload",
+               "case_dp_to_mp_input", "case_broadcast"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_fused_world1(case):
+  launch(case, world=1, device_type="cuda", backend="fused")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["case_basic", "case_ragged_dp", "case_custom_layer",
+                                  "case_cpu_offload"])
+def test_torch_backend_world1(case):
+  launch(case, world=1, device_type="cuda", backend="torch" if case != "case_custom_layer"
+         else "auto")
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.parametrize("case", FUSED_CASES + ["case_column_slice_merge"][:0])
+def test_fused_world2(case):
+  launch(case, world=2, device_type="cuda", backend="fused")
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.parametrize("case", TORCH_CASES)
+def test_nccl_world2(case):
+  launch(case, world=2, device_type="cuda", backend="auto" if case == "case_custom_layer"
+         else "torch")
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.parametrize("case", ["case_column_slice_merge", "case_column_slice_dup_worker",
+                                  "case_all_modes", "case_row_slice"])
+def test_fused_world4(case):
+  if torch.cuda.device_count() < 4:
+    pytest.skip("needs 4 GPUs")
+  launch(case, world=4, device_type="cuda", backend="fused")
