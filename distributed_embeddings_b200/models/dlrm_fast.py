@@ -1,0 +1,249 @@
+"""Hand-scheduled DLRM training step (no autograd on the hot path) + whole-step CUDA graph.
+
+The generic :class:`DLRM` module is convenient but pays for autograd bookkeeping, autocast weight
+casts, index-based interaction and ~150 tiny launches per step.  ``DLRMTrainStep`` runs the same
+math as one static schedule over preallocated buffers:
+
+* dense parameters live in one flat fp32 master buffer with a bf16 shadow (one fused kernel does
+  SGD + re-cast + gradient zeroing); gradients live in one flat buffer (symmetric memory when
+  world > 1) that the one-shot NVLink all-reduce kernel reduces in place;
+* MLP layers: cuBLASLt bf16 GEMMs with fused bias+ReLU epilogues forward, plain GEMMs backward
+  (K padded 13->16 and 479->480 so the tcgen05 library kernels are eligible), fused
+  ReLU-backward+bias-gradient kernel;
+* dot interaction forward/backward: tensor-core kernels; the backward writes the embedding
+  gradient directly into the embedding engine's symmetric gradient buffer;
+* final layer + BCE loss + their backward: one kernel;
+* embedding forward/backward: the fused P2P engine (``parallel/fused.py``);
+* the whole step is captured in a CUDA graph and replayed (launch bound otherwise).
+
+Same model/optimizer as the reference example (examples/dlrm/main.py:76-209): SGD, shared lr.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from ..ops import _native
+from ..parallel.comm import CommContext
+from ..parallel.fused import FusedEngine
+from ..utils.lr_schedule import LearningRateScheduler
+from .dlrm import DLRM
+
+
+def _pad8(n: int) -> int:
+  return (n + 7) // 8 * 8
+
+
+class _Layer:
+  """One linear layer's slices of the flat buffers."""
+
+  def __init__(self, lin: nn.Linear, relu: bool):
+    self.lin = lin
+    self.relu = relu
+    self.out_f, self.in_f = lin.weight.shape
+    self.in_pad = _pad8(self.in_f)
+    self.w_off = self.b_off = 0
+    self.w_numel = self.out_f * self.in_pad
+    self.b_numel = _pad8(self.out_f)
+
+
+class DLRMTrainStep:
+  """Static-schedule training step for :class:`DLRM` on the fused embedding back end."""
+
+  def __init__(self, model: DLRM, lr: float = 24.0, embedding_optimizer: str = "sgd",
+               scheduler: Optional[LearningRateScheduler] = None, use_cuda_graph: bool = True,
+               embedding_optimizer_kwargs: Optional[dict] = None, overlap: bool = True):
+    self.model = model
+    self.emb = model.embedding
+    if self.emb.backend != "fused":
+      raise ValueError("DLRMTrainStep needs the fused embedding back end")
+    self.dev = self.emb.device
+    self.ops = _native.require()
+    self.world = self.emb.world_size
+    self.ctx = CommContext.default(self.dev)
+    self.scheduler = scheduler
+    self.use_cuda_graph = use_cuda_graph
+    self.overlap = overlap
+    self.emb.set_optimizer(embedding_optimizer, lr=lr, **(embedding_optimizer_kwargs or {}))
+    if self.emb._engine is None:
+      self.emb._engine = FusedEngine(self.emb)
+    self.engine: FusedEngine = self.emb._engine
+    self.n_emb = len(model.table_sizes)
+    self.dim = model.embedding_dim
+
+    lins_b = [m for m in model.bottom_mlp.net if isinstance(m, nn.Linear)]
+    lins_t = [m for m in model.top_mlp.net if isinstance(m, nn.Linear)]
+    self.bottom = [_Layer(l, True) for l in lins_b]
+    self.top = [_Layer(l, True) for l in lins_t[:-1]]
+    self.head = _Layer(lins_t[-1], False)
+    if self.head.out_f != 1:
+      raise ValueError("the top MLP must end in a single logit")
+    layers = self.bottom + self.top + [self.head]
+    pos = 0
+    for L in layers:
+      L.w_off = pos
+      pos += L.w_numel
+      L.b_off = pos
+      pos += L.b_numel
+    self.n_flat = pos
+    dev = self.dev
+    self.p32 = torch.zeros(pos, dtype=torch.float32, device=dev)
+    self.p16 = torch.zeros(pos, dtype=torch.bfloat16, device=dev)
+    if self.world > 1:
+      self.gsym = self.ctx.alloc(pos * 4, "dense_grads")
+      self.g32 = self.gsym.view(torch.float32, (pos,))
+    else:
+      self.gsym = None
+      self.g32 = torch.zeros(pos, dtype=torch.float32, device=dev)
+    # move the module parameters into the flat master buffer (strided views keep the module usable)
+    with torch.no_grad():
+      for L in layers:
+        wv = self.p32[L.w_off:L.w_off + L.w_numel].view(L.out_f, L.in_pad)
+        wv[:, :L.in_f].copy_(L.lin.weight)
+        L.lin.weight.data = wv[:, :L.in_f]
+        bv = self.p32[L.b_off:L.b_off + L.out_f]
+        bv.copy_(L.lin.bias)
+        L.lin.bias.data = bv
+        L.w16 = self.p16[L.w_off:L.w_off + L.w_numel].view(L.out_f, L.in_pad)
+        L.b16 = self.p16[L.b_off:L.b_off + L.out_f]
+        L.gw = self.g32[L.w_off:L.w_off + L.w_numel].view(L.out_f, L.in_pad)
+        L.gb = self.g32[L.b_off:L.b_off + L.b_numel]
+      self.p16.copy_(self.p32)
+    self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+    self.lr = float(lr)
+    self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    self._batch = None
+    self._graph = None
+    self._side = torch.cuda.Stream(device=dev) if overlap else None
+
+  # ------------------------------------------------------------------ buffers
+  def _alloc(self, b: int):
+    dev, bf = self.dev, torch.bfloat16
+    self.engine.prepare(b, [1] * self.n_emb, ids64=False)
+    self.cat_stage = self.engine.in_flat[:self.n_emb * b].view(self.n_emb, b)
+    self.num_in = torch.zeros(b, self.bottom[0].in_f, dtype=torch.float32, device=dev)
+    self.lab_in = torch.zeros(b, dtype=torch.float32, device=dev)
+    self.x0 = torch.zeros(b, self.bottom[0].in_pad, dtype=bf, device=dev)
+    for L in self.bottom + self.top:
+      L.y = torch.empty(b, L.out_f, dtype=bf, device=dev)
+      L.dy = torch.empty(b, L.out_f, dtype=bf, device=dev)
+    self.z = torch.zeros(b, self.top[0].in_pad, dtype=bf, device=dev)
+    self.dz = torch.empty(b, self.top[0].in_pad, dtype=bf, device=dev)
+    self._batch = b
+    self._graph = None
+
+  # ------------------------------------------------------------------ the step
+  def _forward(self):
+    ops = self.ops
+    ops.cast_pad(self.num_in, self.x0)
+    x = self.x0
+    for L in self.bottom:
+      torch._addmm_activation(L.b16, x, L.w16.t(), out=L.y)
+      x = L.y
+    emb = self.engine._run_forward()
+    ops.interact_fwd(x, emb, self.n_emb, self.z)
+    x = self.z
+    for L in self.top:
+      torch._addmm_activation(L.b16, x, L.w16.t(), out=L.y)
+      x = L.y
+
+  def _backward(self):
+    ops, eng = self.ops, self.engine
+    b = self._batch
+    last = self.top[-1]
+    self.loss.zero_()
+    H = self.head
+    # final layer + loss + their backward; also the ReLU mask and bias gradient of the layer below
+    ops.head_loss(last.y, H.w16.view(-1), H.b16, self.lab_in, 1.0 / b, last.dy,
+                  H.gw.view(-1), H.gb, last.gb, self.loss, None)
+    # top MLP backward
+    for i in range(len(self.top) - 1, -1, -1):
+      L = self.top[i]
+      x = self.top[i - 1].y if i > 0 else self.z
+      dx = self.top[i - 1].dy if i > 0 else self.dz
+      torch.mm(L.dy.t(), x, out_dtype=torch.float32, out=L.gw)
+      torch.mm(L.dy, L.w16, out=dx)
+      if i > 0:
+        ops.relu_bwd_bias(dx, x, self.top[i - 1].gb)
+    # interaction backward: embedding gradient lands in the engine's (symmetric) gradient buffer
+    hb = self.bottom[-1]
+    ops.interact_bwd(hb.y, eng.out, self.n_emb, self.dz, hb.dy, eng.grad.data_ptr(),
+                     eng.total_width, 1.0)
+    # embedding exchange + fused table update, overlapped with the bottom MLP backward
+    if self._side is not None:
+      self._side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(self._side):
+        eng.backward_inplace()
+    else:
+      eng.backward_inplace()
+    ops.relu_bwd_bias(hb.dy, hb.y, hb.gb)
+    for i in range(len(self.bottom) - 1, -1, -1):
+      L = self.bottom[i]
+      x = self.bottom[i - 1].y if i > 0 else self.x0
+      torch.mm(L.dy.t(), x, out_dtype=torch.float32, out=L.gw)
+      if i > 0:
+        dx = self.bottom[i - 1].dy
+        torch.mm(L.dy, L.w16, out=dx)
+        ops.relu_bwd_bias(dx, x, self.bottom[i - 1].gb)
+    # dense gradient all-reduce (one NVLink kernel, averaged) + fused SGD / re-cast / zero
+    if self.world > 1:
+      self.ctx.allreduce_(self.gsym, self.n_flat, torch.float32, scale=1.0 / self.world)
+    ops.dense_sgd(self.p32, self.p16, self.g32, self.lr_t, 1.0)
+    if self._side is not None:
+      torch.cuda.current_stream().wait_stream(self._side)
+
+  def _step_impl(self):
+    self._forward()
+    self._backward()
+
+  def set_lr(self, lr: float):
+    self.lr = float(lr)
+    self.lr_t.fill_(self.lr)
+    self.engine.update_lr(self.lr)
+
+  def load_batch(self, numerical, categorical, labels):
+    """Copy one batch into the static input buffers (host pinned or device tensors).
+    ``categorical``: ``[n_features, batch]`` tensor (feature major) or list of ``[batch]``."""
+    b = int(numerical.shape[0])
+    if b != self._batch:
+      self._alloc(b)
+    self.num_in.copy_(numerical, non_blocking=True)
+    self.lab_in.copy_(labels.reshape(-1), non_blocking=True)
+    if isinstance(categorical, (list, tuple)):
+      for v, c in zip(self.engine.in_views, categorical):
+        v.copy_(c.reshape(v.shape), non_blocking=True)
+    else:
+      self.cat_stage.copy_(categorical, non_blocking=True)
+
+  def run(self) -> torch.Tensor:
+    """Run one step on the loaded batch; returns the (device) mean loss of the local batch."""
+    if self.scheduler is not None:
+      self.set_lr(self.scheduler.step())
+    if not self.use_cuda_graph:
+      self._step_impl()
+      return self.loss
+    if self._graph is None:
+      # warm up on a side stream (cuBLAS handles / workspaces), then capture.  The learning rate
+      # is zero while warming up so the extra passes leave the weights untouched.
+      self.lr_t.zero_()
+      self.engine.update_lr(0.0)
+      s = torch.cuda.Stream(device=self.dev)
+      s.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(s):
+        for _ in range(2):
+          self._step_impl()
+      torch.cuda.current_stream().wait_stream(s)
+      torch.cuda.synchronize()
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        self._step_impl()
+      self._graph = g
+      self.set_lr(self.lr)
+    self._graph.replay()
+    return self.loss
+
+  def step(self, numerical, categorical, labels) -> torch.Tensor:
+    self.load_batch(numerical, categorical, labels)
+    return self.run()

@@ -385,6 +385,99 @@ void copy_cast_2d(const Tensor& src, int64_t dst_ptr, int64_t dst_stride, bool d
   check_launch();
 }
 
+// ------------------------------------------------------------------ dense-side ops
+void check_bf16_2d(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.dim() == 2 && t.scalar_type() == at::kBFloat16 && t.stride(1) == 1,
+              name, " must be a 2-D bf16 CUDA tensor with unit inner stride");
+}
+
+// z[s] = [strict lower triangle of F F^T | bottom | zero pad], F = [bottom ; emb_0 ; ...]
+void interact_fwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, Tensor z) {
+  check_bf16_2d(bottom, "bottom");
+  check_bf16_2d(emb, "emb");
+  check_bf16_2d(z, "z");
+  c10::cuda::CUDAGuard guard(bottom.device());
+  const int64_t dim = bottom.size(1);
+  TORCH_CHECK(emb.size(1) == n_emb * dim);
+  const int64_t need = (n_emb + 1) * n_emb / 2 + dim;
+  TORCH_CHECK(z.size(1) >= need, "z is too narrow");
+  bool ok = de::launch_interact_fwd(bottom.data_ptr(), bottom.stride(0), emb.data_ptr(),
+                                    emb.stride(0), static_cast<int>(n_emb), static_cast<int>(dim),
+                                    z.data_ptr(), z.stride(0), static_cast<int>(z.size(1)),
+                                    bottom.size(0), sm_count(), cur_stream());
+  TORCH_CHECK(ok, "unsupported interaction shape (n_emb <= 31, dim in {16,32,64,128})");
+  check_launch();
+}
+
+void interact_bwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, const Tensor& dz,
+                  Tensor dbottom, int64_t demb_ptr, int64_t demb_stride, double emb_grad_scale) {
+  check_bf16_2d(bottom, "bottom");
+  check_bf16_2d(emb, "emb");
+  check_bf16_2d(dz, "dz");
+  check_bf16_2d(dbottom, "dbottom");
+  c10::cuda::CUDAGuard guard(bottom.device());
+  const int64_t dim = bottom.size(1);
+  bool ok = de::launch_interact_bwd(bottom.data_ptr(), bottom.stride(0), emb.data_ptr(),
+                                    emb.stride(0), static_cast<int>(n_emb), static_cast<int>(dim),
+                                    dz.data_ptr(), dz.stride(0), dbottom.data_ptr(),
+                                    dbottom.stride(0), reinterpret_cast<void*>(demb_ptr),
+                                    demb_stride, static_cast<float>(emb_grad_scale),
+                                    bottom.size(0), sm_count(), cur_stream());
+  TORCH_CHECK(ok, "unsupported interaction shape (n_emb <= 31, dim in {32,64,128})");
+  check_launch();
+}
+
+void relu_bwd_bias(Tensor dy, const Tensor& y, Tensor db) {
+  check_bf16_2d(dy, "dy");
+  check_bf16_2d(y, "y");
+  TORCH_CHECK(dy.is_contiguous() && y.is_contiguous() && dy.size(1) % 8 == 0);
+  TORCH_CHECK(db.is_cuda() && db.scalar_type() == at::kFloat && db.numel() >= dy.size(1));
+  c10::cuda::CUDAGuard guard(dy.device());
+  de::launch_relu_bwd_bias(dy.data_ptr(), y.data_ptr(), db.data_ptr<float>(), dy.size(0),
+                           static_cast<int>(dy.size(1)), cur_stream());
+  check_launch();
+}
+
+void head_loss(const Tensor& x, const Tensor& w, const Tensor& bias, const Tensor& labels,
+               double inv_batch, Tensor dx, Tensor dw, Tensor db, Tensor dbias_prev,
+               Tensor loss_sum, const c10::optional<Tensor>& logits) {
+  check_bf16_2d(x, "x");
+  TORCH_CHECK(x.is_contiguous() && dx.is_contiguous());
+  TORCH_CHECK(w.scalar_type() == at::kBFloat16 && bias.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(labels.scalar_type() == at::kFloat && labels.is_contiguous());
+  c10::cuda::CUDAGuard guard(x.device());
+  bool ok = de::launch_head_loss(x.data_ptr(), static_cast<int>(x.size(1)), w.data_ptr(),
+                                 bias.data_ptr(), labels.data_ptr<float>(), x.size(0),
+                                 static_cast<float>(inv_batch), dx.data_ptr(),
+                                 dw.data_ptr<float>(), db.data_ptr<float>(),
+                                 dbias_prev.data_ptr<float>(), loss_sum.data_ptr<float>(),
+                                 logits.has_value() ? logits->data_ptr<float>() : nullptr,
+                                 sm_count(), cur_stream());
+  TORCH_CHECK(ok, "head_loss supports K in {64,128,256,512,1024}");
+  check_launch();
+}
+
+void dense_sgd(Tensor p32, Tensor p16, Tensor g32, const Tensor& lr, double grad_scale) {
+  TORCH_CHECK(p32.is_cuda() && p32.scalar_type() == at::kFloat && g32.scalar_type() == at::kFloat &&
+              p16.scalar_type() == at::kBFloat16 && lr.scalar_type() == at::kFloat);
+  TORCH_CHECK(p32.numel() % 4 == 0 && p32.numel() == g32.numel() && p32.numel() == p16.numel());
+  c10::cuda::CUDAGuard guard(p32.device());
+  de::launch_sgd_update(p32.data_ptr<float>(), p16.data_ptr(), g32.data_ptr<float>(),
+                        lr.data_ptr<float>(), static_cast<float>(grad_scale), p32.numel(),
+                        sm_count(), cur_stream());
+  check_launch();
+}
+
+void cast_pad(const Tensor& src, Tensor dst) {
+  TORCH_CHECK(src.is_cuda() && src.scalar_type() == at::kFloat && src.is_contiguous());
+  TORCH_CHECK(dst.scalar_type() == at::kBFloat16 && dst.is_contiguous() &&
+              dst.size(0) == src.size(0) && dst.size(1) >= src.size(1));
+  c10::cuda::CUDAGuard guard(src.device());
+  de::launch_cast_pad(src.data_ptr<float>(), static_cast<int>(src.size(1)), dst.data_ptr(),
+                      static_cast<int>(dst.size(1)), src.size(0), cur_stream());
+  check_launch();
+}
+
 // ------------------------------------------------------------------ symmetric memory (IPC)
 // Buffers that peers map must not come from the caching allocator (its blocks are sub-ranges
 // of larger cudaMalloc segments), so they are cudaMalloc'd here and wrapped with from_blob.
@@ -492,6 +585,22 @@ TORCH_LIBRARY(de_b200, m) {
         &gather_segments);
   m.def("copy_cast_2d(Tensor src, int dst_ptr, int dst_stride, bool dst_bf16, float scale) -> ()",
         &copy_cast_2d);
+  m.def("interact_fwd(Tensor bottom, Tensor emb, int n_emb, Tensor(a!) z) -> ()", &interact_fwd);
+  m.def(
+      "interact_bwd(Tensor bottom, Tensor emb, int n_emb, Tensor dz, Tensor(a!) dbottom, "
+      "int demb_ptr, int demb_stride, float emb_grad_scale) -> ()",
+      &interact_bwd);
+  m.def("relu_bwd_bias(Tensor(a!) dy, Tensor y, Tensor(b!) db) -> ()", &relu_bwd_bias);
+  m.def(
+      "head_loss(Tensor x, Tensor w, Tensor bias, Tensor labels, float inv_batch, Tensor(a!) dx, "
+      "Tensor(b!) dw, Tensor(c!) db, Tensor(d!) dbias_prev, Tensor(e!) loss_sum, Tensor? logits) "
+      "-> ()",
+      &head_loss);
+  m.def(
+      "dense_sgd(Tensor(a!) p32, Tensor(b!) p16, Tensor(c!) g32, Tensor lr, float grad_scale) "
+      "-> ()",
+      &dense_sgd);
+  m.def("cast_pad(Tensor src, Tensor(a!) dst) -> ()", &cast_pad);
   m.def("symm_alloc(int nbytes, int device_index) -> Tensor", &symm_alloc);
   m.def("ipc_get_handle(Tensor buf) -> Tensor", &ipc_get_handle);
   m.def("ipc_open(Tensor handle, int device_index) -> int", &ipc_open);

@@ -123,4 +123,24 @@ void launch_copy_cast_2d(const void* src, int64_t src_stride, void* dst, int64_t
                          int64_t rows, int64_t cols, bool src_bf16, bool dst_bf16, float scale,
                          cudaStream_t stream);
 
+// ---- dense-side kernels (DLRM interaction, fused elementwise + loss + optimizer) ------------
+bool launch_interact_fwd(const void* bottom, int64_t bottom_stride, const void* emb,
+                         int64_t emb_stride, int n_emb, int dim, void* z, int64_t z_stride,
+                         int z_width, int64_t batch, int sm_count, cudaStream_t stream);
+bool launch_interact_bwd(const void* bottom, int64_t bottom_stride, const void* emb,
+                         int64_t emb_stride, int n_emb, int dim, const void* dz,
+                         int64_t dz_stride, void* dbottom, int64_t dbottom_stride, void* demb,
+                         int64_t demb_stride, float emb_grad_scale, int64_t batch, int sm_count,
+                         cudaStream_t stream);
+void launch_relu_bwd_bias(void* dy, const void* y, float* db, int64_t rows, int cols,
+                          cudaStream_t stream);
+bool launch_head_loss(const void* x, int K, const void* w, const void* bias, const float* labels,
+                      int64_t batch, float inv_batch, void* dx, float* dw, float* db,
+                      float* dbias_prev, float* loss_sum, float* logits_out, int sm_count,
+                      cudaStream_t stream);
+void launch_sgd_update(float* p32, void* p16, float* g32, const float* lr_ptr, float grad_scale,
+                       int64_t n, int sm_count, cudaStream_t stream);
+void launch_cast_pad(const float* src, int src_cols, void* dst, int dst_cols, int64_t rows,
+                     cudaStream_t stream);
+
 }  // namespace de

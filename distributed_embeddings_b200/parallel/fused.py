@@ -436,6 +436,15 @@ class FusedEngine:
     grads += self._backward_mp(bf16)
     return grads
 
+  def backward_inplace(self):
+    """Backward when the gradient was already written into ``self.grad`` (e.g. by the fused
+    interaction-backward kernel): barrier + fused table update, nothing else."""
+    if self.W > 1:
+      self.ctx.barrier(2)
+    if len(self.de.dp_layers):
+      raise RuntimeError("backward_inplace does not handle replicated tables")
+    self._backward_mp(self.compute_dtype == torch.bfloat16)
+
   def _backward_mp(self, bf16: bool) -> List[Optional[torch.Tensor]]:
     ops, de = self.ops, self.de
     n_mp = len(self.mp_layers)
