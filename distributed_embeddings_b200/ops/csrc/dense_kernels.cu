@@ -51,18 +51,38 @@ __host__ __device__ constexpr int fwd_warp_bytes(int d) {
   return (kMaxFeat * (d + 8) * 2 > kMaxFeat * 33 * 4) ? kMaxFeat * (d + 8) * 2 : kMaxFeat * 33 * 4;
 }
 
-// Stage F = [bottom ; emb_0 .. emb_{n-1}] (each D bf16) of one sample into smem [32][LD].
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Stage F = [bottom ; emb_0 .. emb_{n-1}] (each D bf16) of one sample into smem [32][LD] with
+// cp.async (LDGSTS): every 16-byte chunk of the sample is in flight before the first wait.
+// Pad rows (> n_emb) are zeroed once by the caller.
 template <int D>
 __device__ __forceinline__ void stage_features(bf16* sF, int LD, const bf16* bottom,
                                                const bf16* emb, int n_emb, int lane) {
   constexpr int kChunks = D / 8;  // 16-byte chunks per row
-  const int total = kMaxFeat * kChunks;
+  const int total = (n_emb + 1) * kChunks;
+#pragma unroll 4
   for (int c = lane; c < total; c += 32) {
     const int row = c / kChunks, ch = c - row * kChunks;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row == 0) v = *reinterpret_cast<const uint4*>(bottom + ch * 8);
-    else if (row <= n_emb) v = *reinterpret_cast<const uint4*>(emb + (row - 1) * D + ch * 8);
-    *reinterpret_cast<uint4*>(sF + row * LD + ch * 8) = v;
+    const bf16* src = row == 0 ? bottom + ch * 8 : emb + (row - 1) * D + ch * 8;
+    cp_async16(sF + row * LD + ch * 8, src);
+  }
+  cp_async_wait_all();
+}
+
+template <int D>
+__device__ __forceinline__ void zero_pad_rows(bf16* sF, int LD, int n_emb, int lane) {
+  constexpr int kChunks = D / 8;
+  for (int c = (n_emb + 1) * kChunks + lane; c < kMaxFeat * kChunks; c += 32) {
+    const int row = c / kChunks, ch = c - row * kChunks;
+    *reinterpret_cast<uint4*>(sF + row * LD + ch * 8) = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -84,6 +104,7 @@ interact_fwd_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
   for (int64_t s = static_cast<int64_t>(blockIdx.x) * kWarps + warp; s < batch;
        s += static_cast<int64_t>(gridDim.x) * kWarps) {
     const bf16* bp = bottom + s * bottom_stride;
+    zero_pad_rows<D>(sF, LD, n_emb, lane);  // the C staging below may alias the pad rows
     stage_features<D>(sF, LD, bp, emb + s * emb_stride, n_emb, lane);
     __syncwarp();
     // lower triangle tiles: m-tile 0 x n-tiles {0,1}; m-tile 1 x n-tiles {0..3}
@@ -153,12 +174,14 @@ interact_bwd_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
   bf16* sG = sF + kMaxFeat * LD;
   const int nf = n_emb + 1;
   const int n_inter = nf * (nf - 1) / 2;
+  zero_pad_rows<D>(sF, LD, n_emb, lane);
 
   for (int64_t s = static_cast<int64_t>(blockIdx.x) * kWarps + warp; s < batch;
        s += static_cast<int64_t>(gridDim.x) * kWarps) {
     stage_features<D>(sF, LD, bottom + s * bottom_stride, emb + s * emb_stride, n_emb, lane);
     const bf16* dzp = dz + s * dz_stride;
-    for (int c = lane; c < kMaxFeat * LDG; c += 32) sG[c] = __float2bfloat16_rn(0.f);
+    for (int c = lane; c < kMaxFeat * LDG / 8; c += 32)
+      reinterpret_cast<uint4*>(sG)[c] = make_uint4(0, 0, 0, 0);
     __syncwarp();
     for (int idx = lane; idx < n_inter; idx += 32) {
       int i = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * idx)) * 0.5f);
@@ -227,37 +250,60 @@ interact_bwd_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
 }
 
 // dy <- dy * (y > 0) (in place) ; db[c] += sum_rows dy   (db fp32, pre-zeroed)
+// Each thread owns 8 columns (one 16-byte vector) and keeps 4 rows in flight; partial column sums
+// are reduced across the block in shared memory, then one atomic per column per block.
+constexpr int kRbUnroll = 4;
 __global__ void __launch_bounds__(256)
 relu_bwd_bias_kernel(bf16* __restrict__ dy, const bf16* __restrict__ y, float* __restrict__ db,
                      int64_t rows, int cols, int rows_per_block) {
-  const int vec_per_row = cols >> 3;
-  const int tpr = vec_per_row;              // threads per row
+  extern __shared__ float s_part[];  // [rows_par][cols]
+  const int tpr = cols >> 3;                // threads per row
   const int rows_par = blockDim.x / tpr;    // rows processed concurrently
   const int tr = threadIdx.x / tpr, tc = threadIdx.x - tr * tpr;
-  if (tr >= rows_par) return;
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int64_t r = r0 + tr; r < r1; r += rows_par) {
-    uint4 g = *reinterpret_cast<const uint4*>(dy + r * cols + tc * 8);
-    const uint4 a = *reinterpret_cast<const uint4*>(y + r * cols + tc * 8);
-    uint32_t* gw = reinterpret_cast<uint32_t*>(&g);
-    const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a);
+  if (tr < rows_par) {
+    for (int64_t r = r0 + tr; r < r1; r += static_cast<int64_t>(rows_par) * kRbUnroll) {
+      uint4 g[kRbUnroll], a[kRbUnroll];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 gf = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&gw[i]));
-      const float2 af = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
-      gf.x = af.x > 0.f ? gf.x : 0.f;
-      gf.y = af.y > 0.f ? gf.y : 0.f;
-      acc[2 * i] += gf.x;
-      acc[2 * i + 1] += gf.y;
-      __nv_bfloat162 h = __floats2bfloat162_rn(gf.x, gf.y);
-      gw[i] = *reinterpret_cast<uint32_t*>(&h);
+      for (int u = 0; u < kRbUnroll; ++u) {
+        const int64_t rr = r + static_cast<int64_t>(u) * rows_par;
+        if (rr < r1) {
+          g[u] = *reinterpret_cast<const uint4*>(dy + rr * cols + tc * 8);
+          a[u] = *reinterpret_cast<const uint4*>(y + rr * cols + tc * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRbUnroll; ++u) {
+        const int64_t rr = r + static_cast<int64_t>(u) * rows_par;
+        if (rr < r1) {
+          uint32_t* gw = reinterpret_cast<uint32_t*>(&g[u]);
+          const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a[u]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 gf = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&gw[i]));
+            const float2 af = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
+            gf.x = af.x > 0.f ? gf.x : 0.f;
+            gf.y = af.y > 0.f ? gf.y : 0.f;
+            acc[2 * i] += gf.x;
+            acc[2 * i + 1] += gf.y;
+            __nv_bfloat162 h = __floats2bfloat162_rn(gf.x, gf.y);
+            gw[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(dy + rr * cols + tc * 8) = g[u];
+        }
+      }
     }
-    *reinterpret_cast<uint4*>(dy + r * cols + tc * 8) = g;
-  }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) atomicAdd(db + tc * 8 + i, acc[i]);
+    for (int i = 0; i < 8; ++i) s_part[tr * cols + tc * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float v = 0.f;
+    for (int t = 0; t < rows_par; ++t) v += s_part[t * cols + c];
+    atomicAdd(db + c, v);
+  }
 }
 
 // Final layer (K -> 1) + BCE-with-logits loss + backward of both, one warp per sample:
@@ -440,11 +486,13 @@ void launch_relu_bwd_bias(void* dy, const void* y, float* db, int64_t rows, int 
                           cudaStream_t stream) {
   if (rows <= 0) return;
   const int tpr = cols / 8;
-  int threads = 256;
-  if (tpr > threads) threads = ((tpr + 31) / 32) * 32;
-  const int rows_per_block = 128;
+  const int threads = 256;  // cols <= 2048
+  const int rows_par = threads / tpr;
+  // ~16 rows per thread (4 batches of 4 in flight); >= 2048 blocks at batch 64k
+  const int rows_per_block = rows_par * kRbUnroll * 4;
   const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
-  relu_bwd_bias_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+  const size_t smem = static_cast<size_t>(rows_par) * cols * sizeof(float);
+  relu_bwd_bias_kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(
       reinterpret_cast<bf16*>(dy), reinterpret_cast<const bf16*>(y), db, rows, cols,
       rows_per_block);
 }

@@ -33,7 +33,7 @@ def test_fast_step_matches_autograd(use_graph):
   t_ref = HybridTrainer(ref, lr=lr, embedding_optimizer="sgd")
   loss_ref = t_ref.step(num, cat, lab)
   t_fast = DLRMTrainStep(fast, lr=lr, embedding_optimizer="sgd", use_cuda_graph=use_graph)
-  loss_fast = t_fast.step(num, torch.stack(cat), lab)
+  loss_fast = t_fast.step(num, torch.stack(cat), lab).clone()
   torch.cuda.synchronize()
   torch.testing.assert_close(loss_fast[0], loss_ref, rtol=2e-2, atol=2e-3)
 

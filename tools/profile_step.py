@@ -19,16 +19,23 @@ p.add_argument("--batch", type=int, default=65536)
 p.add_argument("--steps", type=int, default=5)
 p.add_argument("--optimizer", default="sgd")
 p.add_argument("--out", default="gpurun_out/profile_step.txt")
+p.add_argument("--trainer", default="fast")
 args = p.parse_args()
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 sizes = table_sizes_for(args.model)
 model = DLRM(sizes, device=dev, compute_dtype=torch.bfloat16, backend="fused")
-trainer = HybridTrainer(model, lr=24.0, embedding_optimizer=args.optimizer)
+if args.trainer == "fast":
+  from distributed_embeddings_b200.models.dlrm_fast import DLRMTrainStep
+  trainer = DLRMTrainStep(model, lr=24.0, embedding_optimizer=args.optimizer, use_cuda_graph=False)
+else:
+  trainer = HybridTrainer(model, lr=24.0, embedding_optimizer=args.optimizer)
 b = args.batch
 num = torch.rand(b, 13, device=dev)
 cat = [torch.randint(0, s, (b,), device=dev, dtype=torch.int32) for s in sizes]
+if args.trainer == "fast":
+  cat = torch.stack(cat)
 lab = torch.randint(0, 2, (b, 1), device=dev).float()
 for _ in range(5):
   trainer.step(num, cat, lab)
