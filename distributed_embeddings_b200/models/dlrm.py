@@ -76,7 +76,9 @@ class DLRM(nn.Module):
                test_combiner: bool = False,
                device=None,
                compute_dtype: torch.dtype = torch.bfloat16,
-               backend: str = "auto"):
+               backend: str = "auto",
+               world_size: Optional[int] = None,
+               rank: Optional[int] = None):
     super().__init__()
     if bottom_mlp_dims[-1] != embedding_dim:
       raise ValueError("bottom MLP must end at the embedding width for the dot interaction")
@@ -99,7 +101,9 @@ class DLRM(nn.Module):
                                           data_parallel_threshold=data_parallel_threshold,
                                           device=device,
                                           compute_dtype=compute_dtype,
-                                          backend=backend)
+                                          backend=backend,
+                                          world_size=world_size,
+                                          rank=rank)
     ii, jj = torch.tril_indices(n, n, offset=-1)
     self.register_buffer("tril", (ii * n + jj).to(device), persistent=False)
 

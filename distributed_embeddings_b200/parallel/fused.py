@@ -451,6 +451,10 @@ class FusedEngine:
     if self.mpdesc is None or not any(_weight(l).requires_grad for l in self.mp_layers):
       return [None] * n_mp
     opt = de._fused_optimizer
+    if opt is not None and opt["kind"] != "sgd" and not self.opt_state:
+      self.reset_optimizer_state()
+    if self._tables_dirty:
+      self._refresh_tables()
     B, lb = self.B, self.lb
     # row-slice partial gradients: the gradient of an input lives in grad_buf at the input's
     # output columns for *both* groups, but row descriptors carry rs_buf columns -> patch once

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Single-GPU model on raw (hashed hex) Criteo categorical features with on-the-fly vocabulary
+building: IntegerLookup(100000) -> Embedding(100000, 128) x 26 -> MLP
+(reference examples/criteo/main.py:56-91)."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import torch
+from torch import nn
+
+import distributed_embeddings_b200 as de
+
+
+class CriteoModel(nn.Module):
+
+  def __init__(self, num_cat=26, vocab=100000, dim=128, num_numerical=13, device=None):
+    super().__init__()
+    self.lookups = nn.ModuleList([de.IntegerLookup(vocab, device=device) for _ in range(num_cat)])
+    self.embeddings = nn.ModuleList(
+        [de.Embedding(vocab + 1, dim, device=device) for _ in range(num_cat)])
+    d = num_cat * dim + num_numerical
+    self.mlp = nn.Sequential(nn.Linear(d, 512), nn.ReLU(), nn.Linear(512, 256), nn.ReLU(),
+                             nn.Linear(256, 1)).to(device)
+
+  def forward(self, numerical, categorical):
+    outs = []
+    for lk, emb, c in zip(self.lookups, self.embeddings, categorical):
+      outs.append(emb(lk(c)))
+    return self.mlp(torch.cat(outs + [numerical], dim=1))
+
+
+def synthetic_batches(n_batches, batch, num_cat, device, seed=0):
+  """Raw 32-bit hashed ids with a power-law popularity, like hashed hex Criteo columns."""
+  g = torch.Generator().manual_seed(seed)
+  for _ in range(n_batches):
+    u = torch.rand(batch, num_cat, generator=g)
+    raw = (u.pow(4) * 2**31).to(torch.int64) * 2654435761 % 2**32  # spread over the id space
+    yield (torch.rand(batch, 13, generator=g).to(device), [raw[:, i].to(device)
+                                                            for i in range(num_cat)],
+           torch.randint(0, 2, (batch, 1), generator=g).float().to(device))
+
+
+def main():
+  p = argparse.ArgumentParser()
+  p.add_argument("--batch_size", type=int, default=16384)
+  p.add_argument("--steps", type=int, default=50)
+  p.add_argument("--vocab", type=int, default=100000)
+  args = p.parse_args()
+  device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+  model = CriteoModel(vocab=args.vocab, device=device)
+  dense = [p_ for n, p_ in model.named_parameters() if "embeddings" not in n]
+  sparse = [p_ for n, p_ in model.named_parameters() if "embeddings" in n]
+  opt_d = torch.optim.Adam(dense, lr=1e-3)
+  opt_s = torch.optim.SparseAdam(sparse, lr=1e-3)
+  bce = nn.BCEWithLogitsLoss()
+  for i, (num, cat, lab) in enumerate(synthetic_batches(args.steps, args.batch_size, 26, device)):
+    opt_d.zero_grad()
+    opt_s.zero_grad()
+    loss = bce(model(num, cat), lab)
+    loss.backward()
+    opt_d.step()
+    opt_s.step()
+    if i % 10 == 0:
+      sizes = [lk.vocabulary_size() for lk in model.lookups[:3]]
+      print(f"step {i} loss {float(loss):.4f} vocab sizes (first 3 features) {sizes}")
+
+
+if __name__ == "__main__":
+  main()

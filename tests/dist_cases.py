@@ -402,3 +402,45 @@ def case_hybrid_optimizer(rank, world, device, backend, **kw):
   for t, w in zip(tables, got):
     torch.testing.assert_close(t.detach().cpu(), torch.from_numpy(w), rtol=1e-5, atol=1e-5)
   torch.testing.assert_close(ref.dense.weight, test.dense.weight, rtol=1e-5, atol=1e-5)
+
+
+def case_dlrm_fast_step(rank, world, device, backend, optimizer="sgd", steps=2, **kw):
+  """DLRMTrainStep on `world` ranks (local batches) == DLRMTrainStep in one process on the
+  global batch: same loss, same dense weights, same embedding tables (global-mean contract)."""
+  from distributed_embeddings_b200.models.dlrm import DLRM
+  from distributed_embeddings_b200.models.dlrm_fast import DLRMTrainStep
+  sizes = [200 + 13 * i for i in range(26)]
+  torch.manual_seed(7)
+  ref = DLRM(sizes, device=device, compute_dtype=torch.bfloat16, backend="fused", world_size=1,
+             rank=0)
+  torch.manual_seed(7)
+  test = DLRM(sizes, device=device, compute_dtype=torch.bfloat16, backend="fused")
+  test.load_state_dict({k: v for k, v in ref.state_dict().items() if "embedding" not in k},
+                       strict=False)
+  test.embedding.set_weights(ref.embedding.get_weights(all_ranks=True))
+  gb = 256 * world
+  g = torch.Generator().manual_seed(3)
+  lr = 0.5 if optimizer == "sgd" else 0.05
+  t_ref = DLRMTrainStep(ref, lr=lr, embedding_optimizer=optimizer, use_cuda_graph=False)
+  t_test = DLRMTrainStep(test, lr=lr, embedding_optimizer=optimizer,
+                         use_cuda_graph=kw.get("graph", True))
+  lb = gb // world
+  for _ in range(steps):
+    num = torch.rand(gb, 13, generator=g).to(device)
+    cat = torch.stack([torch.randint(0, s, (gb,), generator=g, dtype=torch.int32)
+                       for s in sizes]).to(device)
+    lab = torch.randint(0, 2, (gb,), generator=g).float().to(device)
+    l_ref = t_ref.step(num, cat, lab).clone()
+    sl = slice(rank * lb, (rank + 1) * lb)
+    l_test = t_test.step(num[sl], cat[:, sl].contiguous(), lab[sl]).clone()
+    dist.all_reduce(l_test)
+    torch.testing.assert_close(l_test / world, l_ref, rtol=1e-2, atol=1e-3)
+  t_test.ctx.check_errors()
+  for (n1, p1), (n2, p2) in zip(ref.named_parameters(), test.named_parameters()):
+    if "embedding" in n1:
+      continue
+    torch.testing.assert_close(p2, p1, rtol=3e-2, atol=3e-3, msg=lambda m: f"{n1}: {m}")
+  w_ref = ref.embedding.get_weights(all_ranks=True)
+  w_test = test.embedding.get_weights(all_ranks=True)
+  for a, b in zip(w_ref, w_test):
+    torch.testing.assert_close(torch.from_numpy(b), torch.from_numpy(a), rtol=3e-2, atol=3e-3)

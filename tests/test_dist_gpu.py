@@ -53,3 +53,16 @@ def test_fused_world4(case):
   if torch.cuda.device_count() < 4:
     pytest.skip("needs 4 GPUs")
   launch(case, world=4, device_type="cuda", backend="fused")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("optimizer", ["sgd", "adagrad"])
+def test_dlrm_fast_world1(optimizer):
+  launch("case_dlrm_fast_step", world=1, device_type="cuda", backend="fused", optimizer=optimizer)
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.parametrize("optimizer", ["sgd", "adagrad", "rowwise_adagrad"])
+def test_dlrm_fast_world2(optimizer):
+  launch("case_dlrm_fast_step", world=2, device_type="cuda", backend="fused", optimizer=optimizer)
