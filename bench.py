@@ -47,6 +47,7 @@ def parse_args():
   p.add_argument("--no-e2e", action="store_true")
   p.add_argument("--column-slice-threshold", type=int, default=None)
   p.add_argument("--cuda-graph", type=int, default=1)
+  p.add_argument("--profile", default=None, help="write a torch.profiler kernel table (rank 0)")
   p.add_argument("--trainer", default="fast", choices=["fast", "autograd"],
                  help="fast = hand-scheduled step + CUDA graph (DLRMTrainStep); autograd = "
                       "nn.Module + HybridTrainer")
@@ -267,6 +268,27 @@ def main():
     launches = _native.launch_count() * args.steps
     torch.cuda.synchronize()
   clocks = sampler.stop() if rank == 0 else None
+
+  if args.profile:
+    from torch.profiler import ProfilerActivity, profile
+    saved = getattr(trainer, "use_cuda_graph", None)
+    if saved is not None:
+      trainer.use_cuda_graph = False
+    for i in range(3):
+      step_from_device(i)
+    sync_all()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+      for i in range(5):
+        step_from_device(i)
+      sync_all()
+    if rank == 0:
+      os.makedirs(os.path.dirname(args.profile) or ".", exist_ok=True)
+      with open(args.profile, "w") as f:
+        f.write(f"# {args.model} world={world} global_batch={gb}, 5 eager steps (no graph)\n")
+        f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40,
+                                          max_name_column_width=70))
+    if saved is not None:
+      trainer.use_cuda_graph = saved
 
   e2e = None
   if not args.no_e2e:
