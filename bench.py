@@ -45,7 +45,8 @@ def parse_args():
   p.add_argument("--lr", type=float, default=24.0)
   p.add_argument("--data-batches", type=int, default=4)
   p.add_argument("--no-e2e", action="store_true")
-  p.add_argument("--column-slice-threshold", type=int, default=None)
+  p.add_argument("--column-slice-threshold", default=None,
+                 help="elements; 'auto' = balance the looked-up columns per rank (slices >= 64 wide)")
   p.add_argument("--cuda-graph", type=int, default=1)
   p.add_argument("--profile", default=None, help="write a torch.profiler kernel table (rank 0)")
   p.add_argument("--trainer", default="fast", choices=["fast", "autograd"],
@@ -143,6 +144,25 @@ def table_sizes_for(model: str):
   raise ValueError(model)
 
 
+def auto_column_slice_threshold(sizes, dim, world):
+  """Pick the column-slice threshold that minimises the most loaded rank's looked-up columns
+  (gather bytes and NVLink bytes per sample are proportional to it); slices stay >= 64 wide."""
+  from distributed_embeddings_b200.parallel.strategy import DistEmbeddingStrategy
+  cfgs = [{"input_dim": s, "output_dim": dim, "combiner": None} for s in sizes]
+  best, best_cols = None, None
+  for thr in [None] + [2**k for k in range(34, 22, -1)]:
+    st = DistEmbeddingStrategy(cfgs, world, "memory_balanced", column_slice_threshold=thr)
+    if any(not st.local_configs[r] for r in range(world)):
+      continue
+    if min(c["output_dim"] for r in range(world) for c in st.local_configs[r]) < 64:
+      continue
+    cols = max(sum(st.local_configs[r][m]["output_dim"] for m in st.local_maps[r])
+               for r in range(world))
+    if best_cols is None or cols < best_cols:
+      best, best_cols = thr, cols
+  return best
+
+
 def main():
   args = parse_args()
   if args.impl == "reference":
@@ -172,8 +192,13 @@ def main():
   gb = args.global_batch
   assert gb % world == 0
   lb = gb // world
+  cst = args.column_slice_threshold
+  if cst == "auto":
+    cst = auto_column_slice_threshold(sizes, 128, world)
+  elif cst is not None:
+    cst = int(cst)
   model = DLRM(sizes, device=device, compute_dtype=compute_dtype, backend=args.backend,
-               column_slice_threshold=args.column_slice_threshold)
+               column_slice_threshold=cst)
   from distributed_embeddings_b200 import broadcast_variables
   broadcast_variables(model)
   use_fast = args.trainer == "fast" and args.backend == "fused"
@@ -325,7 +350,7 @@ def main():
             "global_batch": gb,
             "seq_len": 1,
             "parallelism": f"hybrid: dp{world} dense + table-parallel embeddings "
-                           f"(memory_balanced), backend={args.backend}, trainer={args.trainer}, cuda_graph={int(bool(args.cuda_graph))}",
+                           f"(memory_balanced, column_slice_threshold={cst}), backend={args.backend}, trainer={args.trainer}, cuda_graph={int(bool(args.cuda_graph))}",
             "optimizer": f"{args.optimizer} lr={args.lr} (embedding update fused in backward)",
             "l2_policy": "inputs larger than L2: random rows of "
                          f"{table_gb / world:.1f} GiB tables per GPU vs 126 MB L2",

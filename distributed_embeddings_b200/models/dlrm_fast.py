@@ -137,12 +137,21 @@ class DLRMTrainStep:
   # ------------------------------------------------------------------ the step
   def _forward(self):
     ops = self.ops
+    # the embedding exchange (barrier, id pull, gather + NVLink push, barrier) runs on the side
+    # stream while the bottom MLP runs on the main stream; they meet at the interaction
+    if self._side is not None:
+      self._side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(self._side):
+        emb = self.engine._run_forward()
     ops.cast_pad(self.num_in, self.x0)
     x = self.x0
     for L in self.bottom:
       torch._addmm_activation(L.b16, x, L.w16.t(), out=L.y)
       x = L.y
-    emb = self.engine._run_forward()
+    if self._side is not None:
+      torch.cuda.current_stream().wait_stream(self._side)
+    else:
+      emb = self.engine._run_forward()
     ops.interact_fwd(x, emb, self.n_emb, self.z)
     x = self.z
     for L in self.top:

@@ -478,6 +478,27 @@ void cast_pad(const Tensor& src, Tensor dst) {
   check_launch();
 }
 
+// out[M,N] = act(a[M,K] @ b[N,K]^T + bias) on the hand-written tcgen05 kernel
+void gemm_tn_bias_act(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& bias,
+                      Tensor out, bool relu, int64_t block_n) {
+  check_bf16_2d(a, "a");
+  check_bf16_2d(b, "b");
+  check_bf16_2d(out, "out");
+  TORCH_CHECK(a.size(1) == b.size(1) && out.size(0) == a.size(0) && out.size(1) == b.size(0),
+              "shape mismatch");
+  if (bias.has_value())
+    TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == at::kBFloat16 && bias->is_contiguous() &&
+                bias->numel() == b.size(0));
+  c10::cuda::CUDAGuard guard(a.device());
+  bool ok = de::launch_gemm_tn_bias_act(
+      a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+      bias.has_value() ? bias->data_ptr() : nullptr, out.data_ptr(), out.stride(0),
+      static_cast<int>(a.size(0)), static_cast<int>(b.size(0)), static_cast<int>(a.size(1)), relu,
+      static_cast<int>(block_n), cur_stream());
+  TORCH_CHECK(ok, "gemm_tn_bias_act: unsupported shape/alignment or launch failure");
+  check_launch();
+}
+
 // ------------------------------------------------------------------ symmetric memory (IPC)
 // Buffers that peers map must not come from the caching allocator (its blocks are sub-ranges
 // of larger cudaMalloc segments), so they are cudaMalloc'd here and wrapped with from_blob.
@@ -601,6 +622,10 @@ TORCH_LIBRARY(de_b200, m) {
       "-> ()",
       &dense_sgd);
   m.def("cast_pad(Tensor src, Tensor(a!) dst) -> ()", &cast_pad);
+  m.def(
+      "gemm_tn_bias_act(Tensor a, Tensor b, Tensor? bias, Tensor(a!) out, bool relu, int block_n) "
+      "-> ()",
+      &gemm_tn_bias_act);
   m.def("symm_alloc(int nbytes, int device_index) -> Tensor", &symm_alloc);
   m.def("ipc_get_handle(Tensor buf) -> Tensor", &ipc_get_handle);
   m.def("ipc_open(Tensor handle, int device_index) -> int", &ipc_open);

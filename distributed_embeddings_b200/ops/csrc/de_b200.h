@@ -143,4 +143,9 @@ void launch_sgd_update(float* p32, void* p16, float* g32, const float* lr_ptr, f
 void launch_cast_pad(const float* src, int src_cols, void* dst, int dst_cols, int64_t rows,
                      cudaStream_t stream);
 
+// ---- hand-written tcgen05 / TMA / TMEM GEMM with fused bias + activation epilogue ------------
+bool launch_gemm_tn_bias_act(const void* A, int64_t lda, const void* B, int64_t ldb,
+                             const void* bias, void* C, int64_t ldc, int M, int N, int K,
+                             bool relu, int block_n, cudaStream_t stream);
+
 }  // namespace de

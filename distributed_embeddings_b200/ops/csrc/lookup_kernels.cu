@@ -23,6 +23,11 @@ constexpr int kThreads = 256;
 constexpr int kWarpsPerBlock = kThreads / 32;
 constexpr int kTile = 32;  // samples per warp tile
 constexpr int kUnroll = 4;
+constexpr int kBlocksPerSM = 4;  // 64 registers / thread -> 32 resident warps per SM
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 struct TileCoord {
   int f;        // local input
@@ -87,7 +92,7 @@ __device__ __forceinline__ IdReader<IdT> make_reader(const InputDesc& D, const P
 
 // =============================================================================== forward
 template <typename IdT, typename OutT, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
                   int64_t src_batch, int64_t dst_batch, int64_t dst_stride,
                   const __grid_constant__ PeerPtrs src, const __grid_constant__ PeerPtrs dst,
@@ -191,7 +196,7 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
 // =============================================================================== backward
 // dst_table[row] += scale * w_sample * grad_row   (vector RED, no return value)
 template <typename IdT, typename GradT, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 scatter_add_bwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
                        int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
                        const __grid_constant__ PeerPtrs src, const __grid_constant__ PeerPtrs grad,
@@ -217,6 +222,31 @@ scatter_add_bwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_
     const GradT* grad_base = reinterpret_cast<const GradT*>(grad.p[tc.d]);
     const int64_t i0 = tc.g0 - static_cast<int64_t>(tc.d) * grad_batch;
     const IdReader<IdT> rd = make_reader<IdT>(D, src, src_batch);
+
+    // Pull the table rows of the *next* tile of this warp into L2 so that its reductions find
+    // their lines resident (an atomic that misses L2 waits for the DRAM fill at the slice).
+    {
+      const int64_t tn = t + n_warps;
+      if (tn < total) {
+        const TileCoord nc = decode_tile(tn, n_inputs, n_dst, tiles_per_dst, batch, grad_batch,
+                                         rot);
+        if (lane < nc.nsamp) {
+          const InputDesc& N = descs[nc.f];
+          const IdReader<IdT> nrd = make_reader<IdT>(N, src, src_batch);
+          int nn;
+          const IdT* np = nrd.sample(nc.g0 + lane, nn);
+          const int lines = (N.width * 4 + 127) >> 7;
+          for (int h = 0; h < min(nn, 4); ++h) {
+            const int64_t id = static_cast<int64_t>(np[h]) + N.id_shift;
+            if (static_cast<uint64_t>(id) < static_cast<uint64_t>(N.sub_rows)) {
+              const char* row = reinterpret_cast<const char*>(N.table) +
+                                (N.row_base + id) * N.width * 4;
+              for (int l = 0; l < lines; ++l) prefetch_l2(row + (l << 7));
+            }
+          }
+        }
+      }
+    }
 
     for (int c0 = 0; c0 < nvec; c0 += lpr) {
       const int cv = c0 + li;
@@ -277,7 +307,7 @@ void launch_lookup_fwd(const InputDesc* descs, int n_inputs, int64_t batch, int6
                        const PeerPtrs& dst, int rot, bool ids64, bool out_bf16, bool vec4,
                        int sm_count, cudaStream_t stream) {
   if (n_inputs <= 0 || batch <= 0) return;
-  const int grid = grid_for(count_tiles(n_inputs, batch, dst_batch), sm_count, 8);
+  const int grid = grid_for(count_tiles(n_inputs, batch, dst_batch), sm_count, kBlocksPerSM);
   if (vec4) {
     if (ids64) {
       if (out_bf16) DE_DISPATCH_FWD(int64_t, __nv_bfloat16, 4);
@@ -307,7 +337,7 @@ void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch,
                             bool ids64, bool grad_bf16, bool vec4, int sm_count,
                             cudaStream_t stream) {
   if (n_inputs <= 0 || batch <= 0) return;
-  const int grid = grid_for(count_tiles(n_inputs, batch, grad_batch), sm_count, 8);
+  const int grid = grid_for(count_tiles(n_inputs, batch, grad_batch), sm_count, kBlocksPerSM);
   if (vec4) {
     if (ids64) {
       if (grad_bf16) DE_DISPATCH_BWD(int64_t, __nv_bfloat16, 4);
