@@ -494,7 +494,7 @@ void gemm_tn_bias_act(const Tensor& a, const Tensor& b, const c10::optional<Tens
       a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
       bias.has_value() ? bias->data_ptr() : nullptr, out.data_ptr(), out.stride(0),
       static_cast<int>(a.size(0)), static_cast<int>(b.size(0)), static_cast<int>(a.size(1)), relu,
-      static_cast<int>(block_n), cur_stream());
+      static_cast<int>(block_n), sm_count(), cur_stream());
   TORCH_CHECK(ok, "gemm_tn_bias_act: unsupported shape/alignment or launch failure");
   check_launch();
 }

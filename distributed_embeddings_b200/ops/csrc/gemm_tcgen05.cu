@@ -155,16 +155,21 @@ struct SmemLayout {
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBiasOffset = STAGES * kStageBytes;
-  static constexpr int kBarOffset = kBiasOffset + BLOCK_N * 4;
-  static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int kBarOffset = kBiasOffset + 2 * BLOCK_N * 4;  // bias tile, double buffered
+  static constexpr int kNumBars = 2 * STAGES + 4;                   // full/empty + tmem full/empty x2
+  static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16;
 };
 
+// Persistent kernel: one CTA per SM walks the output tiles (n fastest so that concurrently
+// running CTAs share A rows in L2).  Two TMEM accumulators (2 x BLOCK_N columns) let the epilogue
+// of tile i drain while the MMAs of tile i+1 are already running.
 template <int BLOCK_N, int STAGES, bool RELU>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
                         const __grid_constant__ CUtensorMap tma_b, const bf16* __restrict__ bias,
                         bf16* __restrict__ C, int64_t ldc, int M, int N, int K) {
   using L = SmemLayout<BLOCK_N, STAGES>;
+  constexpr int kTmemCols = 2 * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   // the swizzled tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -172,13 +177,15 @@ gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
   float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOffset);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N;
-  const int m0 = blockIdx.y * BLOCK_M;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_tiles = tiles_n * tiles_m;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -187,11 +194,14 @@ gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);  // every epilogue thread arrives
+    }
     fence_barrier_init();
     fence_proxy_async();
   } else if (warp == 1) {
-    tmem_alloc<BLOCK_N>(tmem_ptr_smem);
+    tmem_alloc<kTmemCols>(tmem_ptr_smem);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -203,16 +213,19 @@ gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * L::kStageBytes;
-        uint8_t* sb = sa + L::kABytes;
-        mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-        tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BLOCK_K, m0);
-        tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BLOCK_K, n0);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BLOCK_K, m0);
+          tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BLOCK_K, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -222,70 +235,91 @@ gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
       constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
         tcgen05_fence_after();
-        const uint32_t sa = smem_addr(smem + stage * L::kStageBytes);
-        const uint32_t sb = sa + L::kABytes;
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_addr(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint64_t da = make_sw128_kmajor_desc(sa + k * UMMA_K * 2);
-          const uint64_t db = make_sw128_kmajor_desc(sb + k * UMMA_K * 2);
-          umma_f16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_sw128_kmajor_desc(sa + k * UMMA_K * 2);
+            const uint64_t db = make_sw128_kmajor_desc(sb + k * UMMA_K * 2);
+            umma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int et = (warp - 2) * 32 + lane;
-    for (int i = et; i < BLOCK_N; i += 128)
-      s_bias[i] = (bias != nullptr && n0 + i < N) ? __bfloat162float(bias[n0 + i]) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const int row = m0 + quad * 32 + lane;
-    bf16* crow = C + static_cast<int64_t>(row) * ldc + n0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      float* sb_tile = s_bias + acc * BLOCK_N;
+      for (int i = et; i < BLOCK_N; i += 128)
+        sb_tile[i] = (bias != nullptr && n0 + i < N) ? __bfloat162float(bias[n0 + i]) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      bf16* crow = C + static_cast<int64_t>(row) * ldc + n0;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c;
-      tmem_ld_32x32b_x32(taddr, v);
-      tmem_ld_wait();
-      if (row < M) {
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + c;
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        if (row < M) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (n0 + c + j < N) {
-            uint32_t packed[4];
+          for (int j = 0; j < 32; j += 8) {
+            if (n0 + c + j < N) {
+              uint32_t packed[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float x0 = __uint_as_float(v[j + 2 * q]) + s_bias[c + j + 2 * q];
-              float x1 = __uint_as_float(v[j + 2 * q + 1]) + s_bias[c + j + 2 * q + 1];
-              if (RELU) {
-                x0 = fmaxf(x0, 0.f);
-                x1 = fmaxf(x1, 0.f);
+              for (int q = 0; q < 4; ++q) {
+                float x0 = __uint_as_float(v[j + 2 * q]) + sb_tile[c + j + 2 * q];
+                float x1 = __uint_as_float(v[j + 2 * q + 1]) + sb_tile[c + j + 2 * q + 1];
+                if (RELU) {
+                  x0 = fmaxf(x0, 0.f);
+                  x1 = fmaxf(x1, 0.f);
+                }
+                __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                packed[q] = *reinterpret_cast<uint32_t*>(&h);
               }
-              __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-              packed[q] = *reinterpret_cast<uint32_t*>(&h);
+              *reinterpret_cast<uint4*>(crow + c + j) =
+                  make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
-            *reinterpret_cast<uint4*>(crow + c + j) =
-                make_uint4(packed[0], packed[1], packed[2], packed[3]);
           }
         }
       }
+      // hand the accumulator back to the MMA warp
+      tcgen05_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(
+                       smem_addr(&tmem_empty_bar[acc]))
+                   : "memory");
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<BLOCK_N>(tmem_base);
+    tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -326,10 +360,11 @@ bool make_tensor_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t co
 
 template <int BLOCK_N, int STAGES>
 bool launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const void* bias, void* C,
-                int64_t ldc, int M, int N, int K, bool relu, cudaStream_t stream) {
+                int64_t ldc, int M, int N, int K, bool relu, int sm_count, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   const size_t smem = L::kTotal + 1024;
-  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + BLOCK_M - 1) / BLOCK_M);
+  const int tiles = ((N + BLOCK_N - 1) / BLOCK_N) * ((M + BLOCK_M - 1) / BLOCK_M);
+  dim3 grid(tiles < sm_count ? tiles : sm_count);
   if (relu) {
     cudaFuncSetAttribute(gemm_tn_bias_act_kernel<BLOCK_N, STAGES, true>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -349,7 +384,7 @@ bool launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const void* bias, 
 // C = act(A B^T + bias). A [M,K] (lda), B [N,K] (ldb), C [M,N] (ldc): bf16, 16-byte aligned rows.
 bool launch_gemm_tn_bias_act(const void* A, int64_t lda, const void* B, int64_t ldb,
                              const void* bias, void* C, int64_t ldc, int M, int N, int K,
-                             bool relu, int block_n, cudaStream_t stream) {
+                             bool relu, int block_n, int sm_count, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return true;
   if ((lda % 8) || (ldb % 8) || (ldc % 8) || (N % 8)) return false;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
@@ -359,8 +394,8 @@ bool launch_gemm_tn_bias_act(const void* A, int64_t lda, const void* B, int64_t 
   alignas(64) CUtensorMap ta, tb;
   if (!make_tensor_map(&ta, A, M, K, lda, BLOCK_M)) return false;
   if (!make_tensor_map(&tb, B, N, K, ldb, bn)) return false;
-  if (bn == 256) return launch_cfg<256, 4>(ta, tb, bias, C, ldc, M, N, K, relu, stream);
-  return launch_cfg<128, 3>(ta, tb, bias, C, ldc, M, N, K, relu, stream);  // 2 CTAs / SM
+  if (bn == 256) return launch_cfg<256, 4>(ta, tb, bias, C, ldc, M, N, K, relu, sm_count, stream);
+  return launch_cfg<128, 6>(ta, tb, bias, C, ldc, M, N, K, relu, sm_count, stream);
 }
 
 }  // namespace de
