@@ -48,6 +48,8 @@ def parse_args():
   p.add_argument("--column-slice-threshold", default=None,
                  help="elements; 'auto' = balance the looked-up columns per rank (slices >= 64 wide)")
   p.add_argument("--cuda-graph", type=int, default=1)
+  p.add_argument("--gemm", default="cublas", choices=["cublas", "fused_dgrad", "tcgen05"],
+                 help="MLP GEMM path of the fast trainer (see models/dlrm_fast.py)")
   p.add_argument("--profile", default=None, help="write a torch.profiler kernel table (rank 0)")
   p.add_argument("--trainer", default="fast", choices=["fast", "autograd"],
                  help="fast = hand-scheduled step + CUDA graph (DLRMTrainStep); autograd = "
@@ -205,7 +207,7 @@ def main():
   if use_fast:
     from distributed_embeddings_b200.models.dlrm_fast import DLRMTrainStep
     trainer = DLRMTrainStep(model, lr=args.lr, embedding_optimizer=args.optimizer,
-                            use_cuda_graph=bool(args.cuda_graph))
+                            use_cuda_graph=bool(args.cuda_graph), gemm=args.gemm)
   else:
     trainer = HybridTrainer(model, lr=args.lr, embedding_optimizer=args.optimizer)
 
@@ -350,7 +352,7 @@ def main():
             "global_batch": gb,
             "seq_len": 1,
             "parallelism": f"hybrid: dp{world} dense + table-parallel embeddings "
-                           f"(memory_balanced, column_slice_threshold={cst}), backend={args.backend}, trainer={args.trainer}, cuda_graph={int(bool(args.cuda_graph))}",
+                           f"(memory_balanced, column_slice_threshold={cst}), backend={args.backend}, trainer={args.trainer}, cuda_graph={int(bool(args.cuda_graph))}, mlp_gemm={args.gemm}",
             "optimizer": f"{args.optimizer} lr={args.lr} (embedding update fused in backward)",
             "l2_policy": "inputs larger than L2: random rows of "
                          f"{table_gb / world:.1f} GiB tables per GPU vs 126 MB L2",

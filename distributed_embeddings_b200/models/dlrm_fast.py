@@ -54,7 +54,14 @@ class DLRMTrainStep:
 
   def __init__(self, model: DLRM, lr: float = 24.0, embedding_optimizer: str = "sgd",
                scheduler: Optional[LearningRateScheduler] = None, use_cuda_graph: bool = True,
-               embedding_optimizer_kwargs: Optional[dict] = None, overlap: bool = True):
+               embedding_optimizer_kwargs: Optional[dict] = None, overlap: bool = True,
+               gemm: str = "cublas"):
+    if gemm not in ("cublas", "fused_dgrad", "tcgen05"):
+      raise ValueError("gemm must be cublas | fused_dgrad | tcgen05")
+    # cublas: cuBLASLt everywhere.  fused_dgrad: forward/wgrad on cuBLASLt, dgrad on the
+    # first-party tcgen05 kernel with the ReLU-backward mask + bias gradient fused in its epilogue.
+    # tcgen05: forward layers on the first-party kernel as well.
+    self.gemm = gemm
     self.model = model
     self.emb = model.embedding
     if self.emb.backend != "fused":
@@ -110,13 +117,37 @@ class DLRMTrainStep:
         L.b16 = self.p16[L.b_off:L.b_off + L.out_f]
         L.gw = self.g32[L.w_off:L.w_off + L.w_numel].view(L.out_f, L.in_pad)
         L.gb = self.g32[L.b_off:L.b_off + L.b_numel]
+        L.w16T = torch.empty(L.in_pad, L.out_f, dtype=torch.bfloat16, device=dev)
       self.p16.copy_(self.p32)
+      self._refresh_transposes()
     self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
     self.lr = float(lr)
     self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
     self._batch = None
     self._graph = None
     self._side = torch.cuda.Stream(device=dev) if overlap else None
+
+  def _refresh_transposes(self):
+    """K-major copies of W^T for the dgrad GEMMs (2.4 M elements, a few microseconds)."""
+    if self.gemm == "cublas":
+      return
+    for L in self.bottom[1:] + self.top[1:]:
+      L.w16T.copy_(L.w16.t())
+
+  def _linear_fwd(self, L, x):
+    if self.gemm == "tcgen05":
+      self.ops.gemm_tn_bias_act(x, L.w16, L.b16, L.y, True, 0)
+    else:
+      torch._addmm_activation(L.b16, x, L.w16.t(), out=L.y)
+    return L.y
+
+  def _dgrad_relu(self, L, x_below, dx, gb_below):
+    """dx = (dy @ W) * (x_below > 0); gb_below += colsum(dx)."""
+    if self.gemm == "cublas":
+      torch.mm(L.dy, L.w16, out=dx)
+      self.ops.relu_bwd_bias(dx, x_below, gb_below)
+    else:
+      self.ops.gemm_dgrad_relu_bias(L.dy, L.w16T, x_below, dx, gb_below, 0)
 
   # ------------------------------------------------------------------ buffers
   def _alloc(self, b: int):
@@ -146,8 +177,7 @@ class DLRMTrainStep:
     ops.cast_pad(self.num_in, self.x0)
     x = self.x0
     for L in self.bottom:
-      torch._addmm_activation(L.b16, x, L.w16.t(), out=L.y)
-      x = L.y
+      x = self._linear_fwd(L, x)
     if self._side is not None:
       torch.cuda.current_stream().wait_stream(self._side)
     else:
@@ -155,8 +185,7 @@ class DLRMTrainStep:
     ops.interact_fwd(x, emb, self.n_emb, self.z)
     x = self.z
     for L in self.top:
-      torch._addmm_activation(L.b16, x, L.w16.t(), out=L.y)
-      x = L.y
+      x = self._linear_fwd(L, x)
 
   def _backward(self):
     ops, eng = self.ops, self.engine
@@ -173,9 +202,10 @@ class DLRMTrainStep:
       x = self.top[i - 1].y if i > 0 else self.z
       dx = self.top[i - 1].dy if i > 0 else self.dz
       torch.mm(L.dy.t(), x, out_dtype=torch.float32, out=L.gw)
-      torch.mm(L.dy, L.w16, out=dx)
       if i > 0:
-        ops.relu_bwd_bias(dx, x, self.top[i - 1].gb)
+        self._dgrad_relu(L, x, dx, self.top[i - 1].gb)
+      else:
+        torch.mm(L.dy, L.w16, out=dx)
     # interaction backward: embedding gradient lands in the engine's (symmetric) gradient buffer
     hb = self.bottom[-1]
     ops.interact_bwd(hb.y, eng.out, self.n_emb, self.dz, hb.dy, eng.grad.data_ptr(),
@@ -193,13 +223,12 @@ class DLRMTrainStep:
       x = self.bottom[i - 1].y if i > 0 else self.x0
       torch.mm(L.dy.t(), x, out_dtype=torch.float32, out=L.gw)
       if i > 0:
-        dx = self.bottom[i - 1].dy
-        torch.mm(L.dy, L.w16, out=dx)
-        ops.relu_bwd_bias(dx, x, self.bottom[i - 1].gb)
+        self._dgrad_relu(L, x, self.bottom[i - 1].dy, self.bottom[i - 1].gb)
     # dense gradient all-reduce (one NVLink kernel, averaged) + fused SGD / re-cast / zero
     if self.world > 1:
       self.ctx.allreduce_(self.gsym, self.n_flat, torch.float32, scale=1.0 / self.world)
     ops.dense_sgd(self.p32, self.p16, self.g32, self.lr_t, 1.0)
+    self._refresh_transposes()
     if self._side is not None:
       torch.cuda.current_stream().wait_stream(self._side)
 

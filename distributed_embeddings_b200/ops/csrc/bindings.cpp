@@ -499,6 +499,27 @@ void gemm_tn_bias_act(const Tensor& a, const Tensor& b, const c10::optional<Tens
   check_launch();
 }
 
+// dx[M,N] = (dy[M,K] @ wt[N,K]^T) * (act > 0); colsum[n] += column sums of dx  (one kernel)
+void gemm_dgrad_relu_bias(const Tensor& dy, const Tensor& wt, const Tensor& act, Tensor dx,
+                          Tensor colsum, int64_t block_n) {
+  check_bf16_2d(dy, "dy");
+  check_bf16_2d(wt, "wt");
+  check_bf16_2d(act, "act");
+  check_bf16_2d(dx, "dx");
+  TORCH_CHECK(dy.size(1) == wt.size(1) && dx.size(0) == dy.size(0) && dx.size(1) == wt.size(0) &&
+              act.size(0) == dx.size(0) && act.size(1) == dx.size(1), "shape mismatch");
+  TORCH_CHECK(colsum.is_cuda() && colsum.scalar_type() == at::kFloat &&
+              colsum.numel() >= dx.size(1));
+  c10::cuda::CUDAGuard guard(dy.device());
+  bool ok = de::launch_gemm_tn_fused(
+      dy.data_ptr(), dy.stride(0), wt.data_ptr(), wt.stride(0), nullptr, dx.data_ptr(),
+      dx.stride(0), static_cast<int>(dy.size(0)), static_cast<int>(wt.size(0)),
+      static_cast<int>(dy.size(1)), 2, act.data_ptr(), act.stride(0), colsum.data_ptr<float>(),
+      static_cast<int>(block_n), sm_count(), cur_stream());
+  TORCH_CHECK(ok, "gemm_dgrad_relu_bias: unsupported shape/alignment or launch failure");
+  check_launch();
+}
+
 // ------------------------------------------------------------------ symmetric memory (IPC)
 // Buffers that peers map must not come from the caching allocator (its blocks are sub-ranges
 // of larger cudaMalloc segments), so they are cudaMalloc'd here and wrapped with from_blob.
@@ -626,6 +647,10 @@ TORCH_LIBRARY(de_b200, m) {
       "gemm_tn_bias_act(Tensor a, Tensor b, Tensor? bias, Tensor(a!) out, bool relu, int block_n) "
       "-> ()",
       &gemm_tn_bias_act);
+  m.def(
+      "gemm_dgrad_relu_bias(Tensor dy, Tensor wt, Tensor act, Tensor(a!) dx, Tensor(b!) colsum, "
+      "int block_n) -> ()",
+      &gemm_dgrad_relu_bias);
   m.def("symm_alloc(int nbytes, int device_index) -> Tensor", &symm_alloc);
   m.def("ipc_get_handle(Tensor buf) -> Tensor", &ipc_get_handle);
   m.def("ipc_open(Tensor handle, int device_index) -> int", &ipc_open);

@@ -144,6 +144,10 @@ void launch_cast_pad(const float* src, int src_cols, void* dst, int dst_cols, in
                      cudaStream_t stream);
 
 // ---- hand-written tcgen05 / TMA / TMEM GEMM with fused bias + activation epilogue ------------
+bool launch_gemm_tn_fused(const void* A, int64_t lda, const void* B, int64_t ldb, const void* bias,
+                          void* C, int64_t ldc, int M, int N, int K, int epi, const void* act,
+                          int64_t ldact, float* colsum, int block_n, int sm_count,
+                          cudaStream_t stream);
 bool launch_gemm_tn_bias_act(const void* A, int64_t lda, const void* B, int64_t ldb,
                              const void* bias, void* C, int64_t ldc, int M, int N, int K,
                              bool relu, int block_n, int sm_count, cudaStream_t stream);

@@ -155,7 +155,9 @@ struct SmemLayout {
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBiasOffset = STAGES * kStageBytes;
-  static constexpr int kBarOffset = kBiasOffset + 2 * BLOCK_N * 4;  // bias tile, double buffered
+  static constexpr int kColsumOffset = kBiasOffset + 2 * BLOCK_N * 4;  // bias tile x2
+  static constexpr int kMaxColsum = 2048;                              // EPI 2: N <= 2048
+  static constexpr int kBarOffset = kColsumOffset + kMaxColsum * 4;
   static constexpr int kNumBars = 2 * STAGES + 4;                   // full/empty + tmem full/empty x2
   static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16;
 };
@@ -163,11 +165,15 @@ struct SmemLayout {
 // Persistent kernel: one CTA per SM walks the output tiles (n fastest so that concurrently
 // running CTAs share A rows in L2).  Two TMEM accumulators (2 x BLOCK_N columns) let the epilogue
 // of tile i drain while the MMAs of tile i+1 are already running.
-template <int BLOCK_N, int STAGES, bool RELU>
+// EPI 0: C = A B^T + bias            EPI 1: C = relu(A B^T + bias)
+// EPI 2 (backward of a ReLU layer's input): C = (A B^T) * (act > 0), colsum[n] += sum_m C[m, n]
+//        i.e. dgrad GEMM + ReLU-backward mask + bias gradient of the layer below in one kernel.
+template <int BLOCK_N, int STAGES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
-                        const __grid_constant__ CUtensorMap tma_b, const bf16* __restrict__ bias,
-                        bf16* __restrict__ C, int64_t ldc, int M, int N, int K) {
+gemm_tn_fused_kernel(const __grid_constant__ CUtensorMap tma_a,
+                     const __grid_constant__ CUtensorMap tma_b, const bf16* __restrict__ bias,
+                     bf16* __restrict__ C, int64_t ldc, int M, int N, int K,
+                     const bf16* __restrict__ act, int64_t ldact, float* __restrict__ colsum) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   constexpr int kTmemCols = 2 * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
@@ -175,6 +181,7 @@ gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOffset);
+  float* s_colsum = reinterpret_cast<float*>(smem + L::kColsumOffset);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
@@ -266,19 +273,25 @@ gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int et = (warp - 2) * 32 + lane;
+    if (EPI == 2) {
+      for (int i = et; i < L::kMaxColsum; i += 128) s_colsum[i] = 0.f;
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       float* sb_tile = s_bias + acc * BLOCK_N;
-      for (int i = et; i < BLOCK_N; i += 128)
-        sb_tile[i] = (bias != nullptr && n0 + i < N) ? __bfloat162float(bias[n0 + i]) : 0.f;
+      if (EPI != 2) {
+        for (int i = et; i < BLOCK_N; i += 128)
+          sb_tile[i] = (bias != nullptr && n0 + i < N) ? __bfloat162float(bias[n0 + i]) : 0.f;
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const int row = m0 + quad * 32 + lane;
       bf16* crow = C + static_cast<int64_t>(row) * ldc + n0;
+      const bf16* arow = EPI == 2 ? act + static_cast<int64_t>(row) * ldact + n0 : nullptr;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         uint32_t v[32];
@@ -286,6 +299,29 @@ gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
             tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + c;
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (EPI == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 a4 = make_uint4(0, 0, 0, 0);
+            if (row < M && n0 + c + j < N) a4 = *reinterpret_cast<const uint4*>(arow + c + j);
+            const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 af = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[q]));
+              f[j + 2 * q] = af.x > 0.f ? f[j + 2 * q] : 0.f;
+              f[j + 2 * q + 1] = af.y > 0.f ? f[j + 2 * q + 1] : 0.f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] += sb_tile[c + j];
+            if (EPI == 1) f[j] = fmaxf(f[j], 0.f);
+          }
+        }
         if (row < M) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -293,13 +329,7 @@ gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
               uint32_t packed[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                float x0 = __uint_as_float(v[j + 2 * q]) + sb_tile[c + j + 2 * q];
-                float x1 = __uint_as_float(v[j + 2 * q + 1]) + sb_tile[c + j + 2 * q + 1];
-                if (RELU) {
-                  x0 = fmaxf(x0, 0.f);
-                  x1 = fmaxf(x1, 0.f);
-                }
-                __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
                 packed[q] = *reinterpret_cast<uint32_t*>(&h);
               }
               *reinterpret_cast<uint4*>(crow + c + j) =
@@ -307,12 +337,34 @@ gemm_tn_bias_act_kernel(const __grid_constant__ CUtensorMap tma_a,
             }
           }
         }
+        if (EPI == 2) {
+          // column sums over the 32 rows of this warp: butterfly transpose-reduce, 31 shuffles;
+          // afterwards lane l holds the sum of column c + l
+#pragma unroll
+          for (int sft = 16; sft >= 1; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int i = 0; i < sft; ++i) {
+              const float send = up ? f[i] : f[i + sft];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, sft);
+              f[i] = (up ? f[i + sft] : f[i]) + recv;
+            }
+          }
+          if (n0 + c + lane < N) atomicAdd(&s_colsum[n0 + c + lane], f[0]);
+        }
       }
       // hand the accumulator back to the MMA warp
       tcgen05_fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(
                        smem_addr(&tmem_empty_bar[acc]))
                    : "memory");
+    }
+    if (EPI == 2) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < N && i < L::kMaxColsum; i += 128) {
+        const float vsum = s_colsum[i];
+        if (vsum != 0.f) atomicAdd(colsum + i, vsum);
+      }
     }
   }
   tcgen05_fence_before();
@@ -358,44 +410,68 @@ bool make_tensor_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t co
   return r == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int STAGES>
-bool launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const void* bias, void* C,
-                int64_t ldc, int M, int N, int K, bool relu, int sm_count, cudaStream_t stream) {
+template <int BLOCK_N, int STAGES, int EPI>
+bool launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const void* bias, void* C,
+                int64_t ldc, int M, int N, int K, const void* act, int64_t ldact, float* colsum,
+                int sm_count, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   const size_t smem = L::kTotal + 1024;
   const int tiles = ((N + BLOCK_N - 1) / BLOCK_N) * ((M + BLOCK_M - 1) / BLOCK_M);
   dim3 grid(tiles < sm_count ? tiles : sm_count);
-  if (relu) {
-    cudaFuncSetAttribute(gemm_tn_bias_act_kernel<BLOCK_N, STAGES, true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    gemm_tn_bias_act_kernel<BLOCK_N, STAGES, true><<<grid, kGemmThreads, smem, stream>>>(
-        ta, tb, reinterpret_cast<const bf16*>(bias), reinterpret_cast<bf16*>(C), ldc, M, N, K);
-  } else {
-    cudaFuncSetAttribute(gemm_tn_bias_act_kernel<BLOCK_N, STAGES, false>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    gemm_tn_bias_act_kernel<BLOCK_N, STAGES, false><<<grid, kGemmThreads, smem, stream>>>(
-        ta, tb, reinterpret_cast<const bf16*>(bias), reinterpret_cast<bf16*>(C), ldc, M, N, K);
-  }
+  cudaFuncSetAttribute(gemm_tn_fused_kernel<BLOCK_N, STAGES, EPI>,
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  gemm_tn_fused_kernel<BLOCK_N, STAGES, EPI><<<grid, kGemmThreads, smem, stream>>>(
+      ta, tb, reinterpret_cast<const bf16*>(bias), reinterpret_cast<bf16*>(C), ldc, M, N, K,
+      reinterpret_cast<const bf16*>(act), ldact, colsum);
   return cudaGetLastError() == cudaSuccess;
+}
+
+template <int BLOCK_N, int STAGES>
+bool launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const void* bias, void* C,
+                int64_t ldc, int M, int N, int K, int epi, const void* act, int64_t ldact,
+                float* colsum, int sm_count, cudaStream_t stream) {
+  if (epi == 0)
+    return launch_one<BLOCK_N, STAGES, 0>(ta, tb, bias, C, ldc, M, N, K, act, ldact, colsum,
+                                          sm_count, stream);
+  if (epi == 1)
+    return launch_one<BLOCK_N, STAGES, 1>(ta, tb, bias, C, ldc, M, N, K, act, ldact, colsum,
+                                          sm_count, stream);
+  return launch_one<BLOCK_N, STAGES, 2>(ta, tb, bias, C, ldc, M, N, K, act, ldact, colsum,
+                                        sm_count, stream);
 }
 
 }  // namespace
 
-// C = act(A B^T + bias). A [M,K] (lda), B [N,K] (ldb), C [M,N] (ldc): bf16, 16-byte aligned rows.
-bool launch_gemm_tn_bias_act(const void* A, int64_t lda, const void* B, int64_t ldb,
-                             const void* bias, void* C, int64_t ldc, int M, int N, int K,
-                             bool relu, int block_n, int sm_count, cudaStream_t stream) {
+// C = epilogue(A B^T). A [M,K] (lda), B [N,K] (ldb), C [M,N] (ldc): bf16, 16-byte aligned rows.
+// epi 0: + bias; 1: relu(+ bias); 2: * (act > 0) and colsum[n] += column sums (N <= 2048).
+bool launch_gemm_tn_fused(const void* A, int64_t lda, const void* B, int64_t ldb, const void* bias,
+                          void* C, int64_t ldc, int M, int N, int K, int epi, const void* act,
+                          int64_t ldact, float* colsum, int block_n, int sm_count,
+                          cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return true;
   if ((lda % 8) || (ldb % 8) || (ldc % 8) || (N % 8)) return false;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
        reinterpret_cast<uintptr_t>(C)) & 15)
     return false;
+  if (epi == 2 && (act == nullptr || colsum == nullptr || N > 2048 || (ldact % 8) ||
+                   (reinterpret_cast<uintptr_t>(act) & 15)))
+    return false;
   const int bn = (block_n == 128 || block_n == 256) ? block_n : (N >= 256 ? 256 : 128);
   alignas(64) CUtensorMap ta, tb;
   if (!make_tensor_map(&ta, A, M, K, lda, BLOCK_M)) return false;
   if (!make_tensor_map(&tb, B, N, K, ldb, bn)) return false;
-  if (bn == 256) return launch_cfg<256, 4>(ta, tb, bias, C, ldc, M, N, K, relu, sm_count, stream);
-  return launch_cfg<128, 6>(ta, tb, bias, C, ldc, M, N, K, relu, sm_count, stream);
+  if (bn == 256)
+    return launch_cfg<256, 4>(ta, tb, bias, C, ldc, M, N, K, epi, act, ldact, colsum, sm_count,
+                              stream);
+  return launch_cfg<128, 6>(ta, tb, bias, C, ldc, M, N, K, epi, act, ldact, colsum, sm_count,
+                            stream);
+}
+
+bool launch_gemm_tn_bias_act(const void* A, int64_t lda, const void* B, int64_t ldb,
+                             const void* bias, void* C, int64_t ldc, int M, int N, int K,
+                             bool relu, int block_n, int sm_count, cudaStream_t stream) {
+  return launch_gemm_tn_fused(A, lda, B, ldb, bias, C, ldc, M, N, K, relu ? 1 : 0, nullptr, 0,
+                              nullptr, block_n, sm_count, stream);
 }
 
 }  // namespace de

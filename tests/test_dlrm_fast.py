@@ -12,8 +12,9 @@ def _make(seed, sizes, dev):
   return DLRM(sizes, device=dev, compute_dtype=torch.bfloat16, backend="fused")
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_fast_step_matches_autograd(use_graph):
+@pytest.mark.parametrize("use_graph,gemm", [(False, "cublas"), (True, "fused_dgrad"),
+                                            (False, "tcgen05"), (True, "tcgen05")])
+def test_fast_step_matches_autograd(use_graph, gemm):
   from distributed_embeddings_b200.models.dlrm_fast import DLRMTrainStep
   from distributed_embeddings_b200.models.trainer import HybridTrainer
   dev = torch.device("cuda", 0)
@@ -32,7 +33,7 @@ def test_fast_step_matches_autograd(use_graph):
 
   t_ref = HybridTrainer(ref, lr=lr, embedding_optimizer="sgd")
   loss_ref = t_ref.step(num, cat, lab)
-  t_fast = DLRMTrainStep(fast, lr=lr, embedding_optimizer="sgd", use_cuda_graph=use_graph)
+  t_fast = DLRMTrainStep(fast, lr=lr, embedding_optimizer="sgd", use_cuda_graph=use_graph, gemm=gemm)
   loss_fast = t_fast.step(num, torch.stack(cat), lab).clone()
   torch.cuda.synchronize()
   torch.testing.assert_close(loss_fast[0], loss_ref, rtol=2e-2, atol=2e-3)

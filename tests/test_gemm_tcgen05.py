@@ -41,3 +41,20 @@ def test_gemm_strided_views_and_no_bias():
   ref = a.float() @ b.float().t()
   torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=0.1)
   assert torch.count_nonzero(big_out[:, :32]) == 0 and torch.count_nonzero(big_out[:, 288:]) == 0
+
+
+@pytest.mark.parametrize("m,n,k", [(4096, 512, 256), (777, 256, 1024), (8192, 1024, 1024),
+                                   (1000, 128, 256)])
+def test_fused_dgrad_relu_bias(m, n, k):
+  """dx = (dy @ W) * (x > 0) and db = colsum(dx) in one tcgen05 kernel (W^T given K-major)."""
+  ops = _native.require()
+  torch.manual_seed(m + n)
+  dy = (torch.randn(m, k, device="cuda") * 0.5).bfloat16()
+  w = (torch.randn(k, n, device="cuda") * 0.1).bfloat16()      # layer weight [out=k, in=n]
+  x = torch.relu(torch.randn(m, n, device="cuda")).bfloat16()   # activation of the layer below
+  dx = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+  colsum = torch.zeros(n, device="cuda")
+  ops.gemm_dgrad_relu_bias(dy, w.t().contiguous(), x, dx, colsum, 0)
+  ref = (dy.float() @ w.float()) * (x > 0)
+  torch.testing.assert_close(dx.float(), ref, rtol=2e-2, atol=5e-2)
+  torch.testing.assert_close(colsum, ref.sum(0), rtol=2e-2, atol=0.5)
