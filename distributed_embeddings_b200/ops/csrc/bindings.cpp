@@ -135,7 +135,7 @@ void segment_update(const Tensor& descs, const Tensor& tables, int64_t n_tables,
                     double beta2, double bias1, double bias2, double grad_scale,
                     double weight_decay, int64_t lr_ptr, const c10::optional<Tensor>& emit_keys,
                     const c10::optional<Tensor>& emit_rows, int64_t max_width, bool grad_bf16,
-                    bool vec4) {
+                    bool vec4, const c10::optional<Tensor>& scratch) {
   c10::cuda::CUDAGuard guard(descs.device());
   de::OptimizerArgs opt;
   opt.kind = static_cast<int32_t>(opt_kind);
@@ -149,6 +149,25 @@ void segment_update(const Tensor& descs, const Tensor& tables, int64_t n_tables,
   opt.weight_decay = static_cast<float>(weight_decay);
   opt.lr_ptr = reinterpret_cast<const float*>(lr_ptr);
   if (opt.kind == de::kOptEmit) TORCH_CHECK(emit_keys.has_value() && emit_rows.has_value());
+  // occurrence-balanced path: immune to id skew (needs a zeroed scratch of >= n_items/32 rows)
+  if (scratch.has_value() && vec4 && max_width <= 128 && opt.kind != de::kOptEmit) {
+    const int64_t n_items = sorted_keys.numel();
+    const int64_t sw = (max_width + 3) / 4 * 4;
+    TORCH_CHECK(scratch->scalar_type() == at::kFloat && scratch->is_contiguous() &&
+                    scratch->numel() >= ((n_items + 31) / 32) * sw,
+                "scratch too small for the balanced update");
+    bool ok = de::launch_balanced_update(
+        reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
+        reinterpret_cast<const de::TableDesc*>(tables.data_ptr()), static_cast<int>(n_tables),
+        batch, grad_batch, grad_stride, to_peers(grad_ptrs), sorted_keys.data_ptr<int64_t>(),
+        reinterpret_cast<const uint32_t*>(sorted_items.data_ptr<int>()), n_items,
+        seg_start.data_ptr<int64_t>(), n_unique.data_ptr<int64_t>(), opt,
+        scratch->data_ptr<float>(), static_cast<int>(sw), static_cast<int>(max_width), grad_bf16,
+        sm_count(), cur_stream());
+    TORCH_CHECK(ok, "balanced update launch failed");
+    check_launch();
+    return;
+  }
   de::launch_segment_update(
       reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
       reinterpret_cast<const de::TableDesc*>(tables.data_ptr()), static_cast<int>(n_tables), batch,
@@ -283,7 +302,7 @@ std::tuple<Tensor, Tensor> embedding_lookup_grad(const Tensor& values,
   std::vector<int64_t> gp = {reinterpret_cast<int64_t>(grad.data_ptr())};
   segment_update(dd, td, 1, batch, batch, gstride, gp, std::get<0>(sorted), std::get<1>(sorted),
                  std::get<2>(sorted), std::get<3>(sorted), de::kOptEmit, 0, 0, 0, 0, 1, 1, 1.0, 0, 0,
-                 emit_keys, emit_rows, width, bf16, vec4);
+                 emit_keys, emit_rows, width, bf16, vec4, c10::nullopt);
   // sizing the IndexedSlices-style result needs the unique count on the host (compat path only)
   int64_t n_unique = std::get<3>(sorted).item<int64_t>();
   if (n_unique > 0) {
@@ -594,7 +613,8 @@ TORCH_LIBRARY(de_b200, m) {
       "int grad_stride, int[] grad_ptrs, Tensor sorted_keys, Tensor sorted_items, "
       "Tensor seg_start, Tensor n_unique, int opt_kind, float lr, float eps, float beta1, "
       "float beta2, float bias1, float bias2, float grad_scale, float weight_decay, int lr_ptr, "
-      "Tensor? emit_keys, Tensor? emit_rows, int max_width, bool grad_bf16, bool vec4) -> ()",
+      "Tensor? emit_keys, Tensor? emit_rows, int max_width, bool grad_bf16, bool vec4, "
+      "Tensor? scratch) -> ()",
       &segment_update);
   m.def(
       "embedding_lookup_fwd(Tensor param, Tensor values, Tensor? offsets, int hotness, int batch, "

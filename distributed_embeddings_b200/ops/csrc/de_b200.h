@@ -92,6 +92,14 @@ void launch_segment_update(const InputDesc* descs, const TableDesc* tables, int 
                            int64_t* emit_keys, float* emit_rows, int max_width, bool grad_bf16,
                            bool vec4, int sm_count, cudaStream_t stream);
 
+bool launch_balanced_update(const InputDesc* descs, const TableDesc* tables, int n_tables,
+                            int64_t batch, int64_t grad_batch, int64_t grad_stride,
+                            const PeerPtrs& grad, const int64_t* sorted_keys,
+                            const uint32_t* sorted_items, int64_t n_items,
+                            const int64_t* seg_start, const int64_t* n_unique,
+                            const OptimizerArgs& opt, float* scratch, int scratch_width,
+                            int max_width, bool grad_bf16, int sm_count, cudaStream_t stream);
+
 // ---- misc ---------------------------------------------------------------------------------
 void launch_row_to_split(const int64_t* coo_indices, int64_t nnz, int64_t num_rows,
                          int64_t* row_splits, cudaStream_t stream);

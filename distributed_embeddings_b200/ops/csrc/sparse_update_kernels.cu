@@ -262,6 +262,218 @@ segment_update_kernel(const InputDesc* __restrict__ descs, const TableDesc* __re
   }
 }
 
+// ------------------------------------------------------------------ occurrence-balanced update
+// Power-law ids put a large share of all look-ups on a handful of rows (alpha = 1.05: ~7 % on one
+// row), so "one lane group per unique row" serialises.  Here the *sorted occurrence list* is cut
+// into fixed chunks of kChunk positions; a lane group walks one chunk, summing runs of equal
+// keys.  A run that is a whole segment is applied directly; a segment that crosses a chunk border
+// is accumulated with vector RED into the scratch row of the chunk where it starts and applied by
+// `finalize_crossing_kernel`.  Work per lane group is constant no matter how skewed the ids are.
+constexpr int kChunk = 32;
+
+template <typename GradT>
+__device__ __forceinline__ FVec<4> load_weighted_grad(const InputDesc* __restrict__ descs,
+                                                      uint32_t item, int64_t batch,
+                                                      int64_t grad_batch, int64_t grad_stride,
+                                                      const PeerPtrs& grad, int col, float& w,
+                                                      bool& ok) {
+  const int f = static_cast<int>(item / batch);
+  const int64_t g = item - static_cast<int64_t>(f) * batch;
+  const InputDesc& D = descs[f];
+  const int64_t d = g / grad_batch;
+  const int64_t i = g - d * grad_batch;
+  w = 1.f;
+  if (D.combiner == 1) {
+    const int n = D.offsets ? static_cast<int>(D.offsets[g + 1] - D.offsets[g]) : D.hotness;
+    w = 1.f / static_cast<float>(n);
+  }
+  ok = col < D.width;
+  FVec<4> x;
+  x.zero();
+  if (ok)
+    x = ld_act<GradT, 4>(reinterpret_cast<const GradT*>(grad.p[d]) + i * grad_stride + D.dst_col +
+                         col);
+  return x;
+}
+
+// start position of the segment that contains sorted position `pos` (binary search, O(log u))
+__device__ __forceinline__ int64_t segment_start_of(const int64_t* __restrict__ seg_start,
+                                                    int64_t n_unique, int64_t pos) {
+  int64_t lo = 0, hi = n_unique;
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (seg_start[mid] <= pos) lo = mid;
+    else hi = mid;
+  }
+  return seg_start[lo];
+}
+
+__device__ __forceinline__ int find_table(const TableDesc* __restrict__ tables, int n_tables,
+                                          int64_t key) {
+  int m = 0;
+  while (m + 1 < n_tables && tables[m + 1].key_base <= key) ++m;
+  return m;
+}
+
+// Apply the optimizer to one row given the complete (scaled) gradient fragment of this lane.
+__device__ __forceinline__ void apply_row(const TableDesc& T, const OptimizerArgs& opt,
+                                          int64_t row, int col, FVec<4> g, int lpr,
+                                          unsigned group_mask) {
+  const bool col_ok = col < T.width;
+  float row_state = 0.f;
+  if (opt.kind == kOptRowwiseAdagrad) {
+    float ss = 0.f;
+    if (col_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ss = fmaf(g.v[i], g.v[i], ss);
+    }
+    for (int off = lpr >> 1; off > 0; off >>= 1) ss += __shfl_xor_sync(group_mask, ss, off);
+    float* st = reinterpret_cast<float*>(T.state0) + row;
+    row_state = *st + ss / static_cast<float>(T.width);
+    __syncwarp(group_mask);
+    if (col == 0) *st = row_state;
+  }
+  if (col_ok) apply_update<4>(T, opt, row, col, g, row_state);
+}
+
+template <typename GradT>
+__global__ void __launch_bounds__(kThreads)
+balanced_update_kernel(const InputDesc* __restrict__ descs, const TableDesc* __restrict__ tables,
+                       int n_tables, int lpr, int64_t batch, int64_t grad_batch,
+                       int64_t grad_stride, const __grid_constant__ PeerPtrs grad,
+                       const int64_t* __restrict__ sorted_keys,
+                       const uint32_t* __restrict__ sorted_items, int64_t n_items,
+                       const int64_t* __restrict__ seg_start,
+                       const int64_t* __restrict__ n_unique_p,
+                       const __grid_constant__ OptimizerArgs opt_in, float* __restrict__ scratch,
+                       int scratch_width) {
+  OptimizerArgs opt = opt_in;
+  if (opt.lr_ptr != nullptr) opt.lr = *opt.lr_ptr;
+  const int64_t n_unique = *n_unique_p;
+  const int64_t sentinel = tables[n_tables - 1].key_base + tables[n_tables - 1].rows;
+  const int lane = threadIdx.x & 31;
+  const int rpw = 32 / lpr;
+  const int sub = lane / lpr, li = lane - sub * lpr;
+  const int col = li * 4;
+  const unsigned group_mask = (lpr == 32) ? 0xffffffffu : (((1u << lpr) - 1u) << (sub * lpr));
+  const int64_t n_chunks = (n_items + kChunk - 1) / kChunk;
+  const int64_t group = ((static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5) * rpw +
+                        sub;
+  const int64_t n_groups = static_cast<int64_t>(gridDim.x) * (kThreads / 32) * rpw;
+
+  for (int64_t chunk = group; chunk < n_chunks; chunk += n_groups) {
+    const int64_t k0 = chunk * kChunk;
+    const int64_t k1 = min(n_items, k0 + kChunk);
+    FVec<4> acc;
+    acc.zero();
+    int64_t run_key = sorted_keys[k0];
+    int64_t run_start = k0;
+    for (int64_t kb = k0; kb < k1; kb += kUnroll) {
+      int64_t key[kUnroll];
+      FVec<4> x[kUnroll];
+      float w[kUnroll];
+      bool ok[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t k = kb + u;
+        key[u] = sentinel;
+        ok[u] = false;
+        w[u] = 0.f;
+        x[u].zero();
+        if (k < k1) {
+          key[u] = sorted_keys[k];
+          if (key[u] < sentinel)
+            x[u] = load_weighted_grad<GradT>(descs, sorted_items[k], batch, grad_batch,
+                                             grad_stride, grad, col, w[u], ok[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t k = kb + u;
+        if (k >= k1) break;
+        if (key[u] != run_key) {
+          // flush the finished run [run_start, k)
+          if (run_key < sentinel) {
+            const bool start_done = run_start > k0 || k0 == 0 || sorted_keys[k0 - 1] != run_key;
+            const int m = find_table(tables, n_tables, run_key);
+            const TableDesc T = tables[m];
+            FVec<4> g = acc;
+            g.scale(opt.grad_scale);
+            if (start_done) {
+              apply_row(T, opt, run_key - T.key_base, col, g, lpr, group_mask);
+            } else if (col < T.width) {
+              // continues a segment that started in an earlier chunk: that chunk owns the slot
+              const int64_t s = segment_start_of(seg_start, n_unique, k0);
+              red_add_f32<4>(scratch + (s / kChunk) * scratch_width + col, g);
+            }
+          }
+          acc.zero();
+          run_key = key[u];
+          run_start = k;
+        }
+        if (ok[u]) acc.fma(w[u], x[u]);
+      }
+    }
+    // last run of the chunk
+    if (run_key < sentinel) {
+      const bool start_done = run_start > k0 || k0 == 0 || sorted_keys[k0 - 1] != run_key;
+      const bool end_done = k1 == n_items || sorted_keys[k1] != run_key;
+      const int m = find_table(tables, n_tables, run_key);
+      const TableDesc T = tables[m];
+      FVec<4> g = acc;
+      g.scale(opt.grad_scale);
+      if (start_done && end_done) {
+        apply_row(T, opt, run_key - T.key_base, col, g, lpr, group_mask);
+      } else if (col < T.width) {
+        const int64_t s = start_done ? run_start : segment_start_of(seg_start, n_unique, k0);
+        red_add_f32<4>(scratch + (s / kChunk) * scratch_width + col, g);
+      }
+    }
+  }
+}
+
+// One lane group per chunk: if a segment that crosses the chunk's end border starts in this chunk,
+// its complete gradient sits in the chunk's scratch row: apply it, then clear the row.
+__global__ void __launch_bounds__(kThreads)
+finalize_crossing_kernel(const TableDesc* __restrict__ tables, int n_tables, int lpr,
+                         const int64_t* __restrict__ sorted_keys, int64_t n_items,
+                         const __grid_constant__ OptimizerArgs opt_in, float* __restrict__ scratch,
+                         int scratch_width) {
+  OptimizerArgs opt = opt_in;
+  if (opt.lr_ptr != nullptr) opt.lr = *opt.lr_ptr;
+  const int64_t sentinel = tables[n_tables - 1].key_base + tables[n_tables - 1].rows;
+  const int lane = threadIdx.x & 31;
+  const int rpw = 32 / lpr;
+  const int sub = lane / lpr, li = lane - sub * lpr;
+  const int col = li * 4;
+  const unsigned group_mask = (lpr == 32) ? 0xffffffffu : (((1u << lpr) - 1u) << (sub * lpr));
+  const int64_t n_chunks = (n_items + kChunk - 1) / kChunk;
+  const int64_t group = ((static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5) * rpw +
+                        sub;
+  const int64_t n_groups = static_cast<int64_t>(gridDim.x) * (kThreads / 32) * rpw;
+  for (int64_t chunk = group; chunk < n_chunks; chunk += n_groups) {
+    const int64_t k0 = chunk * kChunk;
+    const int64_t last = min(n_items, k0 + kChunk) - 1;
+    if (last + 1 >= n_items) continue;
+    const int64_t key = sorted_keys[last];
+    if (key >= sentinel || sorted_keys[last + 1] != key) continue;  // nothing crosses the border
+    // the crossing segment belongs to this chunk only if it starts inside it
+    if (sorted_keys[k0] == key && k0 > 0 && sorted_keys[k0 - 1] == key) continue;
+    const int m = find_table(tables, n_tables, key);
+    const TableDesc T = tables[m];
+    float* sp = scratch + chunk * scratch_width + col;
+    FVec<4> g;
+    g.zero();
+    if (col < T.width) {
+      g = ld_f32_rw<4>(sp);
+      FVec<4> z;
+      z.zero();
+      st_f32<4>(sp, z);
+    }
+    apply_row(T, opt, key - T.key_base, col, g, lpr, group_mask);
+  }
+}
+
 int grid_cap(int64_t work_warps, int sm_count, int per_sm) {
   int64_t blocks = (work_warps + (kThreads / 32) - 1) / (kThreads / 32);
   int64_t cap = static_cast<int64_t>(sm_count) * per_sm;
@@ -358,6 +570,36 @@ void launch_segment_update(const InputDesc* descs, const TableDesc* tables, int 
     if (grad_bf16) DE_DISPATCH_SEG(__nv_bfloat16, 1);
     else DE_DISPATCH_SEG(float, 1);
   }
+}
+
+// Occurrence-balanced variant (vec4, tables up to 128 columns wide, fused optimizers only).
+// `scratch` holds ceil(n_items / 32) rows of `scratch_width` floats and must be all zero on entry;
+// it is all zero again on exit.
+bool launch_balanced_update(const InputDesc* descs, const TableDesc* tables, int n_tables,
+                            int64_t batch, int64_t grad_batch, int64_t grad_stride,
+                            const PeerPtrs& grad, const int64_t* sorted_keys,
+                            const uint32_t* sorted_items, int64_t n_items,
+                            const int64_t* seg_start, const int64_t* n_unique,
+                            const OptimizerArgs& opt, float* scratch, int scratch_width,
+                            int max_width, bool grad_bf16, int sm_count, cudaStream_t stream) {
+  if (n_items <= 0 || n_tables <= 0) return true;
+  if (max_width > 128 || max_width % 4 || scratch_width % 4 || opt.kind == kOptEmit) return false;
+  int lpr = 1;
+  while (lpr < max_width / 4 && lpr < 32) lpr <<= 1;
+  const int rpw = 32 / lpr;
+  const int64_t n_chunks = (n_items + kChunk - 1) / kChunk;
+  const int grid = grid_cap((n_chunks + rpw - 1) / rpw, sm_count, 8);
+  if (grad_bf16)
+    balanced_update_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(
+        descs, tables, n_tables, lpr, batch, grad_batch, grad_stride, grad, sorted_keys,
+        sorted_items, n_items, seg_start, n_unique, opt, scratch, scratch_width);
+  else
+    balanced_update_kernel<float><<<grid, kThreads, 0, stream>>>(
+        descs, tables, n_tables, lpr, batch, grad_batch, grad_stride, grad, sorted_keys,
+        sorted_items, n_items, seg_start, n_unique, opt, scratch, scratch_width);
+  finalize_crossing_kernel<<<grid, kThreads, 0, stream>>>(tables, n_tables, lpr, sorted_keys,
+                                                          n_items, opt, scratch, scratch_width);
+  return cudaGetLastError() == cudaSuccess;
 }
 
 }  // namespace de

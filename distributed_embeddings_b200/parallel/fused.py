@@ -475,7 +475,7 @@ class FusedEngine:
                          self.grad_ptrs, keys, items, seg, n_unique, _OPT_KIND[opt["kind"]],
                          opt["lr"], opt["eps"], opt["beta1"], opt["beta2"], bias1, bias2,
                          de.mp_grad_scale, opt["weight_decay"], self.lr_t.data_ptr(), None, None,
-                         self.max_width, bf16, self.vec4)
+                         self.max_width, bf16, self.vec4, self._balanced_scratch())
       return [None] * n_mp
     # no fused optimizer: materialise deduplicated sparse gradients (reference semantics)
     emit_keys = torch.empty(self.n_items, dtype=torch.int64, device=self.device)
@@ -483,7 +483,7 @@ class FusedEngine:
     ops.segment_update(self._bwd_desc(), self.tdesc, n_mp, B, lb, self.total_width, self.grad_ptrs,
                        keys, items, seg, n_unique, _native.OPT_EMIT, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0,
                        de.mp_grad_scale, 0.0, 0, emit_keys, emit_rows, self.max_width, bf16,
-                       self.vec4)
+                       self.vec4, None)
     nu = int(n_unique.item())
     emit_keys, emit_rows = emit_keys[:nu], emit_rows[:nu]
     bases = [int(x) for x in self.tdesc_np["key_base"]] + [self.total_rows]
@@ -497,6 +497,18 @@ class FusedEngine:
       out.append(torch.sparse_coo_tensor(ids, rows, size=tuple(w.shape), is_coalesced=True,
                                          check_invariants=False))
     return out
+
+  def _balanced_scratch(self):
+    """Zero-initialised scratch rows of the occurrence-balanced update (kept zero by the
+    kernels); None selects the per-unique-row kernel (wide tables)."""
+    if not self.vec4 or self.max_width > 128 or self.n_items == 0:
+      return None
+    sw = (self.max_width + 3) // 4 * 4
+    need = ((self.n_items + 31) // 32) * sw
+    cur = getattr(self, "_scratch", None)
+    if cur is None or cur.numel() < need:
+      self._scratch = torch.zeros(need, dtype=torch.float32, device=self.device)
+    return self._scratch
 
   def _bwd_desc(self):
     """Backward descriptors: same as forward but row-slice inputs read their gradient at the
