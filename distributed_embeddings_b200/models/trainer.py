@@ -32,7 +32,8 @@ class HybridTrainer:
   def __init__(self, model: nn.Module, lr: float = 24.0, embedding_optimizer: str = "sgd",
                scheduler: Optional[LearningRateScheduler] = None, momentum: float = 0.0,
                embedding_optimizer_kwargs: Optional[dict] = None,
-               loss_fn: Optional[Callable] = None):
+               loss_fn: Optional[Callable] = None, use_cuda_graph: bool = False,
+               graph_warmup_steps: int = 3):
     self.model = model
     self.emb = model.embedding
     self.emb.set_optimizer(embedding_optimizer, lr=lr, **(embedding_optimizer_kwargs or {}))
@@ -47,6 +48,16 @@ class HybridTrainer:
     self.opt = torch.optim.SGD(self.dense_params, lr=lr, momentum=momentum,
                                foreach=dev.type == "cuda")
     self.loss_fn = loss_fn or nn.BCEWithLogitsLoss()
+    # whole-step CUDA graph: the first `graph_warmup_steps` calls run eagerly (real steps), the
+    # next call captures forward + backward + all-reduce + optimizer and every call replays it
+    self.use_cuda_graph = use_cuda_graph and dev.type == "cuda"
+    self.graph_warmup_steps = graph_warmup_steps
+    self._calls = 0
+    self._graph = None
+    self._static = None
+    # autograd caches each leaf's AccumulateGrad node together with the stream it was first used
+    # on; warm-up and capture therefore have to run on the same (non-default) stream
+    self._gstream = torch.cuda.Stream(device=dev) if self.use_cuda_graph else None
 
   def set_lr(self, lr: float):
     self.lr = lr
@@ -57,6 +68,32 @@ class HybridTrainer:
   def step(self, numerical, categorical, labels, staged: bool = False) -> torch.Tensor:
     if self.scheduler is not None:
       self.set_lr(self.scheduler.step())
+    self._calls += 1
+    if not self.use_cuda_graph or staged:
+      return self._step_eager(numerical, categorical, labels, staged)
+    if self._calls <= self.graph_warmup_steps:
+      self._gstream.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(self._gstream):
+        loss = self._step_eager(numerical, categorical, labels, staged)
+      torch.cuda.current_stream().wait_stream(self._gstream)
+      return loss
+    if self._static is None:
+      self._static = (numerical.clone(), [c.clone() for c in categorical], labels.clone())
+    sn, sc, sl = self._static
+    sn.copy_(numerical, non_blocking=True)
+    sl.copy_(labels, non_blocking=True)
+    for d, c in zip(sc, categorical):
+      d.copy_(c, non_blocking=True)
+    if self._graph is None:
+      torch.cuda.synchronize()
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g, stream=self._gstream):
+        self._static_loss = self._step_eager(sn, sc, sl, False)
+      self._graph = g
+    self._graph.replay()
+    return self._static_loss
+
+  def _step_eager(self, numerical, categorical, labels, staged: bool = False) -> torch.Tensor:
     self.bucket.zero_()
     logits = self.model(numerical, categorical, staged=staged) if staged else \
         self.model(numerical, categorical)

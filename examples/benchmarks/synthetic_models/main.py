@@ -42,6 +42,7 @@ def main():
   p.add_argument("--backend", default="auto", choices=["auto", "fused", "torch"])
   p.add_argument("--row_scale", type=float, default=1.0, help="shrink tables (smoke runs)")
   p.add_argument("--device", default=None)
+  p.add_argument("--cuda_graph", type=int, default=1, help="capture the whole step in a CUDA graph")
   args = p.parse_args()
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -80,7 +81,8 @@ def main():
 
   if args.embedding_api == "de":
     lr = {"sgd": 0.03, "adagrad": 0.001, "rowwise_adagrad": 0.001, "adam": 0.001}[args.optimizer]
-    trainer = HybridTrainer(model, lr=lr, embedding_optimizer=args.optimizer)
+    trainer = HybridTrainer(model, lr=lr, embedding_optimizer=args.optimizer,
+                            use_cuda_graph=bool(args.cuda_graph) and use_cuda)
     step = lambda num, cat, lab: trainer.step(num, cat, lab)
   else:
     opt = {"sgd": lambda ps: torch.optim.SGD(ps, lr=0.03),
