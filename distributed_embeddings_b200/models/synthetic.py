@@ -99,6 +99,11 @@ def _interact(x: torch.Tensor, stride: int) -> torch.Tensor:
 class _SyntheticBase(nn.Module):
 
   def _build_mlp(self, config: ModelConfig, in_dim: int, device):
+    # pad the first layer's fan-in to a multiple of 8 elements (16 bytes of bf16) so the GEMM is
+    # eligible for the TMA / tcgen05 library kernels; the pad inputs are zeros
+    self._in_dim = in_dim
+    self._in_pad = (-in_dim) % 8
+    in_dim += self._in_pad
     layers, d = [], in_dim
     for h in config.mlp_sizes:
       layers += [nn.Linear(d, h, device=device), nn.ReLU()]
@@ -111,9 +116,12 @@ class _SyntheticBase(nn.Module):
     x = torch.cat(outs, dim=1) if isinstance(outs, (list, tuple)) else outs
     if self.interact_stride is not None:
       x = _interact(x.float(), self.interact_stride)
+    dt = self.compute_dtype if amp else numerical.dtype
+    parts = [x.to(dt), numerical.to(dt)]
+    if self._in_pad:
+      parts.append(torch.zeros(x.shape[0], self._in_pad, dtype=dt, device=x.device))
     with torch.autocast("cuda", dtype=self.compute_dtype, enabled=amp):
-      x = torch.cat([x.to(numerical.dtype), numerical], dim=1)
-      return self.mlp(x)
+      return self.mlp(torch.cat(parts, dim=1))
 
   def dense_parameters(self):
     return [p for p in self.parameters() if not getattr(p, "de_local", False)]

@@ -309,10 +309,37 @@ void launch_gather_segments(const int64_t* segs, int n_seg, const PeerPtrs& src,
                                                                   reinterpret_cast<int32_t*>(dst));
 }
 
+// 16-byte fast path: same dtype, unit scale, everything 16-byte aligned
+__global__ void copy_2d_vec16_kernel(const uint4* __restrict__ src, int64_t src_stride16,
+                                     uint4* __restrict__ dst, int64_t dst_stride16, int64_t rows,
+                                     int64_t cols16) {
+  const int64_t n = rows * cols16;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    const int64_t r = i / cols16, c = i - r * cols16;
+    dst[r * dst_stride16 + c] = src[r * src_stride16 + c];
+  }
+}
+
 void launch_copy_cast_2d(const void* src, int64_t src_stride, void* dst, int64_t dst_stride,
                          int64_t rows, int64_t cols, bool src_bf16, bool dst_bf16, float scale,
                          cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return;
+  {
+    const int64_t per16 = src_bf16 ? 8 : 4;
+    if (src_bf16 == dst_bf16 && scale == 1.0f && cols % per16 == 0 && src_stride % per16 == 0 &&
+        dst_stride % per16 == 0 &&
+        ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+      const int64_t n = rows * (cols / per16);
+      int64_t blocks = (n + 255) / 256;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      copy_2d_vec16_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+          reinterpret_cast<const uint4*>(src), src_stride / per16, reinterpret_cast<uint4*>(dst),
+          dst_stride / per16, rows, cols / per16);
+      return;
+    }
+  }
   const int threads = 256;
   int64_t blocks = (rows * cols + threads - 1) / threads;
   if (blocks > 148 * 8) blocks = 148 * 8;

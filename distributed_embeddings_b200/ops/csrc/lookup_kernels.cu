@@ -161,13 +161,15 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
           FVec<VEC> acc;
           acc.zero();
           int h = 0, hits = 0;
-          for (; h + kUnroll <= n; h += kUnroll) {
-            int64_t id[kUnroll];
-            FVec<VEC> x[kUnroll];
+          constexpr int kHotUnroll = 8;  // rows of one sample in flight
+          for (; h + kHotUnroll <= n; h += kHotUnroll) {
+            int64_t id[kHotUnroll];
+            FVec<VEC> x[kHotUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) id[u] = static_cast<int64_t>(p[h + u]) + D.id_shift;
+            for (int u = 0; u < kHotUnroll; ++u)
+              id[u] = static_cast<int64_t>(p[h + u]) + D.id_shift;
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
+            for (int u = 0; u < kHotUnroll; ++u) {
               x[u].zero();
               if (static_cast<uint64_t>(id[u]) < static_cast<uint64_t>(D.sub_rows)) {
                 x[u] = ld_f32<VEC>(table + (D.row_base + id[u]) * W + col);
@@ -175,7 +177,7 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
               }
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) acc.add(x[u]);
+            for (int u = 0; u < kHotUnroll; ++u) acc.add(x[u]);
           }
           for (; h < n; ++h) {
             const int64_t id = static_cast<int64_t>(p[h]) + D.id_shift;

@@ -270,6 +270,7 @@ segment_update_kernel(const InputDesc* __restrict__ descs, const TableDesc* __re
 // is accumulated with vector RED into the scratch row of the chunk where it starts and applied by
 // `finalize_crossing_kernel`.  Work per lane group is constant no matter how skewed the ids are.
 constexpr int kChunk = 32;
+constexpr int kBalUnroll = 8;  // gradient rows in flight per lane group
 
 template <typename GradT>
 __device__ __forceinline__ FVec<4> load_weighted_grad(const InputDesc* __restrict__ descs,
@@ -368,13 +369,13 @@ balanced_update_kernel(const InputDesc* __restrict__ descs, const TableDesc* __r
     acc.zero();
     int64_t run_key = sorted_keys[k0];
     int64_t run_start = k0;
-    for (int64_t kb = k0; kb < k1; kb += kUnroll) {
-      int64_t key[kUnroll];
-      FVec<4> x[kUnroll];
-      float w[kUnroll];
-      bool ok[kUnroll];
+    for (int64_t kb = k0; kb < k1; kb += kBalUnroll) {
+      int64_t key[kBalUnroll];
+      FVec<4> x[kBalUnroll];
+      float w[kBalUnroll];
+      bool ok[kBalUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < kBalUnroll; ++u) {
         const int64_t k = kb + u;
         key[u] = sentinel;
         ok[u] = false;
@@ -388,7 +389,7 @@ balanced_update_kernel(const InputDesc* __restrict__ descs, const TableDesc* __r
         }
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < kBalUnroll; ++u) {
         const int64_t k = kb + u;
         if (k >= k1) break;
         if (key[u] != run_key) {
