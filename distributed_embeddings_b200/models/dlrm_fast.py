@@ -126,6 +126,9 @@ class DLRMTrainStep:
     self._batch = None
     self._graph = None
     self._side = torch.cuda.Stream(device=dev) if overlap else None
+    # weight-gradient GEMMs are off the critical path (head -> dgrads -> interaction -> embedding
+    # backward): they run on a second side stream and join before the all-reduce
+    self._wstream = torch.cuda.Stream(device=dev) if overlap else None
 
   def _refresh_transposes(self):
     """K-major copies of W^T for the dgrad GEMMs (2.4 M elements, a few microseconds)."""
@@ -140,6 +143,15 @@ class DLRMTrainStep:
     else:
       torch._addmm_activation(L.b16, x, L.w16.t(), out=L.y)
     return L.y
+
+  def _wgrad(self, L, x):
+    """gw = dy^T @ x (fp32), on the weight-gradient stream."""
+    if self._wstream is None:
+      torch.mm(L.dy.t(), x, out_dtype=torch.float32, out=L.gw)
+      return
+    self._wstream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(self._wstream):
+      torch.mm(L.dy.t(), x, out_dtype=torch.float32, out=L.gw)
 
   def _dgrad_relu(self, L, x_below, dx, gb_below):
     """dx = (dy @ W) * (x_below > 0); gb_below += colsum(dx)."""
@@ -201,7 +213,7 @@ class DLRMTrainStep:
       L = self.top[i]
       x = self.top[i - 1].y if i > 0 else self.z
       dx = self.top[i - 1].dy if i > 0 else self.dz
-      torch.mm(L.dy.t(), x, out_dtype=torch.float32, out=L.gw)
+      self._wgrad(L, x)
       if i > 0:
         self._dgrad_relu(L, x, dx, self.top[i - 1].gb)
       else:
@@ -221,10 +233,12 @@ class DLRMTrainStep:
     for i in range(len(self.bottom) - 1, -1, -1):
       L = self.bottom[i]
       x = self.bottom[i - 1].y if i > 0 else self.x0
-      torch.mm(L.dy.t(), x, out_dtype=torch.float32, out=L.gw)
+      self._wgrad(L, x)
       if i > 0:
         self._dgrad_relu(L, x, self.bottom[i - 1].dy, self.bottom[i - 1].gb)
     # dense gradient all-reduce (one NVLink kernel, averaged) + fused SGD / re-cast / zero
+    if self._wstream is not None:
+      torch.cuda.current_stream().wait_stream(self._wstream)
     if self.world > 1:
       self.ctx.allreduce_(self.gsym, self.n_flat, torch.float32, scale=1.0 / self.world)
     ops.dense_sgd(self.p32, self.p16, self.g32, self.lr_t, 1.0)
