@@ -28,6 +28,7 @@ from torch import nn
 from ..ops import _native
 from ..parallel.comm import CommContext
 from ..parallel.fused import FusedEngine
+from ..utils import nvtx
 from ..utils.lr_schedule import LearningRateScheduler
 from .dlrm import DLRM
 
@@ -247,8 +248,10 @@ class DLRMTrainStep:
       torch.cuda.current_stream().wait_stream(self._side)
 
   def _step_impl(self):
-    self._forward()
-    self._backward()
+    with nvtx.range("dlrm_forward"):
+      self._forward()
+    with nvtx.range("dlrm_backward_update"):
+      self._backward()
 
   def set_lr(self, lr: float):
     self.lr = float(lr)

@@ -361,15 +361,19 @@ class DistributedEmbedding(nn.Module):
   def dp_parameters(self) -> List[nn.Parameter]:
     return [p for p in self.parameters() if not getattr(p, "de_local", False)]
 
-  def _check_plan_consistency(self):
+  def _check_plan_consistency(self, batch_size: Optional[int] = None):
+    """Once, at the first forward: all ranks must run the same plan and the same batch size
+    (the reference gathers the batch sizes in build(), dist_model_parallel.py:1170-1177)."""
     if self._plan_checked or self.world_size == 1 or not dist_ready():
       self._plan_checked = True
       return
-    fp = self.strategy.fingerprint()
-    got: List[Optional[str]] = [None] * self.world_size
-    dist.all_gather_object(got, fp, group=self.group)
-    if len(set(got)) != 1:
-      raise RuntimeError(f"sharding plans differ across ranks: {got}")
+    got: List[Optional[tuple]] = [None] * self.world_size
+    dist.all_gather_object(got, (self.strategy.fingerprint(), batch_size), group=self.group)
+    if len({g[0] for g in got}) != 1:
+      raise RuntimeError(f"sharding plans differ across ranks: {[g[0][:12] for g in got]}")
+    sizes = {g[1] for g in got}
+    if len(sizes) != 1:
+      raise ValueError(f"All input need to have same batchsize. got {sizes}.")
     self._plan_checked = True
 
   # ---------------------------------------------------------------------------- forward
@@ -406,7 +410,7 @@ class DistributedEmbedding(nn.Module):
       list of ``[local_batch, width]`` tensors in input order (or the concatenation).
     """
     inputs = self._validate_inputs(inputs)
-    self._check_plan_consistency()
+    self._check_plan_consistency(_batch_of(inputs[0]) if inputs else None)
     if self.backend == "fused":
       from .fused import FusedEngine  # pylint: disable=import-outside-toplevel
       if self._engine is None:

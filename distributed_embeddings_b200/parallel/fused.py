@@ -32,6 +32,7 @@ import torch
 from ..ops import _native
 from ..ops._native import INPUT_DESC, TABLE_DESC
 from ..ops.ragged import RaggedIds
+from ..utils import nvtx
 from .comm import CommContext
 
 _OPT_KIND = {"sgd": _native.OPT_SGD, "adagrad": _native.OPT_ADAGRAD,
@@ -381,6 +382,10 @@ class FusedEngine:
     return list(torch.split(out, self.out_widths, dim=1))
 
   def _run_forward(self):
+    with nvtx.range("emb_forward"):
+      return self._run_forward_impl()
+
+  def _run_forward_impl(self):
     ops, W, rank = self.ops, self.W, self.rank
     B, lb = self.B, self.lb
     bf16 = self.compute_dtype == torch.bfloat16
@@ -446,6 +451,10 @@ class FusedEngine:
     self._backward_mp(self.compute_dtype == torch.bfloat16)
 
   def _backward_mp(self, bf16: bool) -> List[Optional[torch.Tensor]]:
+    with nvtx.range("emb_backward_update"):
+      return self._backward_mp_impl(bf16)
+
+  def _backward_mp_impl(self, bf16: bool) -> List[Optional[torch.Tensor]]:
     ops, de = self.ops, self.de
     n_mp = len(self.mp_layers)
     if self.mpdesc is None or not any(_weight(l).requires_grad for l in self.mp_layers):

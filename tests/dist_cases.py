@@ -444,3 +444,50 @@ def case_dlrm_fast_step(rank, world, device, backend, optimizer="sgd", steps=2, 
   w_test = test.embedding.get_weights(all_ranks=True)
   for a, b in zip(w_ref, w_test):
     torch.testing.assert_close(torch.from_numpy(b), torch.from_numpy(a), rtol=3e-2, atol=3e-3)
+
+
+def case_checkpoint_resharding(rank, world, device, backend, **kw):
+  """Weights written under one sharding load under another and give identical outputs; also
+  through .npy files (memory mapped) and with use_lock."""
+  import os
+  import tempfile
+  torch.manual_seed(50)
+  sizes = [[300, 8], [40, 16], [1000, 8], [64, 4], [500, 16], [9, 8]]
+  a = EmbeddingListModel(sizes, distribute=True, strategy="memory_balanced", combiner="sum",
+                         column_slice_threshold=1500, device=device, backend=backend)
+  b = EmbeddingListModel(sizes, distribute=True, strategy="basic", combiner="sum",
+                         row_slice_threshold=7000, data_parallel_threshold=100, device=device,
+                         backend=backend)
+  ref = [np.random.RandomState(3 + i).rand(r, w).astype(np.float32) for i, (r, w) in
+         enumerate(sizes)]
+  a.dist_embeddings.set_weights(ref)
+  got = a.dist_embeddings.get_weights(all_ranks=True)
+  for x, y in zip(ref, got):
+    np.testing.assert_array_equal(x, y)
+  # rank-0-only gather, files, lock-step loading
+  only0 = a.dist_embeddings.get_weights()
+  assert (len(only0) == len(sizes)) == (rank == 0)
+  tmp = tempfile.mkdtemp(prefix=f"ckpt_r{rank}_")
+  paths = []
+  for i, w in enumerate(got):
+    path = os.path.join(tmp, f"t{i}.npy")
+    np.save(path, w)
+    paths.append(path)
+  b.dist_embeddings.set_weights(paths, chunk=1024, use_lock=True)
+  for x, y in zip(ref, b.dist_embeddings.get_weights(all_ranks=True)):
+    np.testing.assert_array_equal(x, y)
+  glob = gen_inputs(51, 8 * world, sizes, hotness=3, device=device)
+  inputs = [slice_batch(x, rank, 8) for x in glob]
+  oa = torch.cat(a.dist_embeddings(inputs), 1)
+  ob = torch.cat(b.dist_embeddings(inputs), 1)
+  torch.testing.assert_close(oa, ob, rtol=1e-6, atol=1e-6)
+
+
+def case_batch_mismatch(rank, world, device, backend, **kw):
+  import pytest
+  sizes = [[10, 4], [10, 4]]
+  model = EmbeddingListModel(sizes, distribute=True, device=device, backend=backend)
+  bs = 4 + (2 if rank == 1 else 0)
+  ids = [torch.zeros(bs, dtype=torch.int64, device=device) for _ in sizes]
+  with pytest.raises(ValueError, match="same batchsize"):
+    model.dist_embeddings(ids)

@@ -10,7 +10,7 @@ CASES = [
     "case_column_slice_threshold", "case_fewer_tables_than_workers", "case_custom_layer",
     "case_multihot_dp", "case_multihot_mp", "case_multihot_mean", "case_ragged_dp",
     "case_cpu_offload", "case_int32_ids", "case_dp_to_mp_input", "case_broadcast", "case_errors",
-    "case_hybrid_optimizer",
+    "case_hybrid_optimizer", "case_checkpoint_resharding", "case_batch_mismatch",
 ]
 
 
@@ -20,7 +20,8 @@ def test_world2(case):
 
 
 @pytest.mark.parametrize("case", ["case_column_slice_merge", "case_column_slice_dup_worker",
-                                  "case_all_modes", "case_basic", "case_row_slice"])
+                                  "case_all_modes", "case_basic", "case_row_slice",
+                                  "case_checkpoint_resharding"])
 def test_world4(case):
   launch(case, world=4)
 
