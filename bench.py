@@ -255,8 +255,15 @@ def main():
 
   def step_e2e(i):
     n, c, l = pool[i % len(pool)]
-    if use_fast:  # H2D straight into the static (symmetric) input buffers, then graph replay
-      loss = trainer.step(n, c, l)
+    if use_fast:
+      # asynchronous input pipeline: batch i was copied (pinned host -> device) on the copy
+      # stream while step i-1 ran; batch i+1 is enqueued now and overlaps step i
+      if i == 0:
+        trainer.prefetch(n, c, l)
+      loss = trainer.run_prefetched()
+      if i + 1 < args.steps:
+        n2, c2, l2 = pool[(i + 1) % len(pool)]
+        trainer.prefetch(n2, c2, l2)
       slot = i & 1
       loss_host[slot].copy_(loss.reshape(1), non_blocking=True)
       loss_events[slot].record()
@@ -336,8 +343,13 @@ def main():
 
   e2e = None
   if not args.no_e2e:
-    for i in range(3):
-      step_e2e(i)
+    if use_fast:  # build + capture the staged schedule outside the timed region
+      for i in range(3):
+        trainer.prefetch(*pool[i % len(pool)])
+        trainer.run_prefetched()
+    else:
+      for i in range(3):
+        step_e2e(i)
     e2e_ms = timed(step_e2e, args.steps)
     e2e = {"value": gb * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
            "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d_bytes * world,

@@ -177,10 +177,24 @@ class DLRMTrainStep:
     self.dz = torch.empty(b, self.top[0].in_pad, dtype=bf, device=dev)
     self._batch = b
     self._graph = None
+    # double-buffered device staging for the asynchronous input pipeline (prefetch())
+    self._stage = [(torch.zeros_like(self.cat_stage), torch.zeros_like(self.num_in),
+                    torch.zeros_like(self.lab_in)) for _ in range(2)]
+    self._slot_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    self._slot_host = torch.tensor([[0], [1]], dtype=torch.int32).pin_memory()
+    self._h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+    self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    self._prefetched = 0   # batches handed to prefetch()
+    self._consumed_n = 0   # batches run
+    self._use_stage = False
 
   # ------------------------------------------------------------------ the step
   def _forward(self):
     ops = self.ops
+    if self._use_stage:
+      a, b_ = self._stage
+      ops.select_copy([a[0], a[1], a[2]], [b_[0], b_[1], b_[2]],
+                      [self.cat_stage, self.num_in, self.lab_in], self._slot_dev)
     # the embedding exchange (barrier, id pull, gather + NVLink push, barrier) runs on the side
     # stream while the bottom MLP runs on the main stream; they meet at the interaction
     if self._side is not None:
@@ -271,6 +285,41 @@ class DLRMTrainStep:
         v.copy_(c.reshape(v.shape), non_blocking=True)
     else:
       self.cat_stage.copy_(categorical, non_blocking=True)
+
+  def prefetch(self, numerical, categorical, labels):
+    """Asynchronous input pipeline: enqueue the H2D copy of the *next* batch (pinned host
+    tensors; ``categorical`` as ``[n_features, batch]`` int32) on the copy stream while the
+    current step runs.  Consume with :meth:`run_prefetched` in the same order."""
+    b = int(numerical.shape[0])
+    if b != self._batch:
+      self._alloc(b)
+    if not self._use_stage:
+      self._use_stage = True
+      self._graph = None  # the staged schedule starts with select_copy
+      self._copy_stream = torch.cuda.Stream(device=self.dev)
+    slot = self._prefetched & 1
+    cs = self._copy_stream
+    if self._prefetched >= 2:
+      cs.wait_event(self._consumed[slot])  # the step that used this slot has been enqueued & done
+    with torch.cuda.stream(cs):
+      st = self._stage[slot]
+      st[0].copy_(categorical, non_blocking=True)
+      st[1].copy_(numerical, non_blocking=True)
+      st[2].copy_(labels.reshape(-1), non_blocking=True)
+      self._h2d_done[slot].record(cs)
+    self._prefetched += 1
+
+  def run_prefetched(self) -> torch.Tensor:
+    """Run one step on the oldest prefetched batch."""
+    assert self._consumed_n < self._prefetched, "call prefetch() first"
+    slot = self._consumed_n & 1
+    main = torch.cuda.current_stream()
+    main.wait_event(self._h2d_done[slot])
+    self._slot_dev.copy_(self._slot_host[slot], non_blocking=True)
+    loss = self.run()
+    self._consumed[slot].record(main)
+    self._consumed_n += 1
+    return loss
 
   def run(self) -> torch.Tensor:
     """Run one step on the loaded batch; returns the (device) mean loss of the local batch."""

@@ -392,6 +392,31 @@ void gather_segments(const Tensor& segs, at::IntArrayRef src_ptrs, Tensor dst,
   check_launch();
 }
 
+// dst[k] <- (slot ? src1[k] : src0[k]); the slot is read on the device (graph replay friendly)
+void select_copy(at::TensorList src0, at::TensorList src1, at::TensorList dst,
+                 const Tensor& slot_flag) {
+  TORCH_CHECK(src0.size() == dst.size() && src1.size() == dst.size() && dst.size() <= 4);
+  TORCH_CHECK(slot_flag.is_cuda() && slot_flag.scalar_type() == at::kInt);
+  const void* s0[4];
+  const void* s1[4];
+  void* d[4];
+  int64_t nb[4];
+  for (size_t i = 0; i < dst.size(); ++i) {
+    TORCH_CHECK(src0[i].is_contiguous() && src1[i].is_contiguous() && dst[i].is_contiguous());
+    nb[i] = dst[i].numel() * dst[i].element_size();
+    TORCH_CHECK(src0[i].numel() * src0[i].element_size() == nb[i] &&
+                src1[i].numel() * src1[i].element_size() == nb[i] && nb[i] % 16 == 0,
+                "select_copy segments must match and be multiples of 16 bytes");
+    s0[i] = src0[i].data_ptr();
+    s1[i] = src1[i].data_ptr();
+    d[i] = dst[i].data_ptr();
+  }
+  c10::cuda::CUDAGuard guard(slot_flag.device());
+  de::launch_select_copy(s0, s1, d, nb, static_cast<int>(dst.size()), slot_flag.data_ptr<int>(),
+                         sm_count(), cur_stream());
+  check_launch();
+}
+
 void copy_cast_2d(const Tensor& src, int64_t dst_ptr, int64_t dst_stride, bool dst_bf16,
                   double scale) {
   TORCH_CHECK(src.is_cuda() && src.dim() == 2 && src.stride(1) == 1);
@@ -645,6 +670,8 @@ TORCH_LIBRARY(de_b200, m) {
       &allreduce);
   m.def("gather_segments(Tensor segs, int[] src_ptrs, Tensor(a!) dst, int max_seg_elems) -> ()",
         &gather_segments);
+  m.def("select_copy(Tensor[] src0, Tensor[] src1, Tensor(a!)[] dst, Tensor slot_flag) -> ()",
+        &select_copy);
   m.def("copy_cast_2d(Tensor src, int dst_ptr, int dst_stride, bool dst_bf16, float scale) -> ()",
         &copy_cast_2d);
   m.def("interact_fwd(Tensor bottom, Tensor emb, int n_emb, Tensor(a!) z) -> ()", &interact_fwd);

@@ -226,6 +226,28 @@ __global__ void gather_segments_kernel(const int64_t* __restrict__ segs,
     dp[i] = sp[i];
 }
 
+// Double-buffered input staging for graph-replayed steps: copies the active staging slot
+// (chosen by a device-resident flag, so one captured graph serves both slots) into the static
+// input buffers.  All sizes are multiples of 16 bytes.
+struct SelectSegs {
+  const uint4* src[2][4];
+  uint4* dst[4];
+  int64_t n16[4];
+  int count;
+};
+__global__ void select_copy_kernel(const __grid_constant__ SelectSegs segs,
+                                   const int* __restrict__ slot_flag) {
+  const int slot = (*slot_flag) & 1;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int s = 0; s < segs.count; ++s) {
+    const uint4* src = segs.src[slot][s];
+    uint4* dst = segs.dst[s];
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < segs.n16[s];
+         i += stride)
+      dst[i] = src[i];
+  }
+}
+
 template <typename S, typename D>
 __global__ void copy_cast_2d_kernel(const S* __restrict__ src, int64_t src_stride,
                                     D* __restrict__ dst, int64_t dst_stride, int64_t rows,
@@ -291,6 +313,25 @@ void launch_allreduce_multimem(void* mc_ptr, const PeerPtrs& flags, uint32_t* ep
     allreduce_multimem_kernel<false><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         mc_ptr, flags, epoch, epoch + 1, rank, world, n_vec16, scale, channel, timeout_cycles,
         error_flag);
+}
+
+void launch_select_copy(const void* const* src0, const void* const* src1, void* const* dst,
+                        const int64_t* nbytes, int count, const int* slot_flag, int sm_count,
+                        cudaStream_t stream) {
+  SelectSegs segs;
+  segs.count = count > 4 ? 4 : count;
+  int64_t total = 0;
+  for (int i = 0; i < segs.count; ++i) {
+    segs.src[0][i] = reinterpret_cast<const uint4*>(src0[i]);
+    segs.src[1][i] = reinterpret_cast<const uint4*>(src1[i]);
+    segs.dst[i] = reinterpret_cast<uint4*>(dst[i]);
+    segs.n16[i] = nbytes[i] / 16;
+    total += segs.n16[i];
+  }
+  if (total == 0) return;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > sm_count * 4) blocks = sm_count * 4;
+  select_copy_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(segs, slot_flag);
 }
 
 void launch_gather_segments(const int64_t* segs, int n_seg, const PeerPtrs& src, void* dst,

@@ -53,3 +53,37 @@ def test_fast_step_matches_autograd(use_graph, gemm):
   loss2 = t_fast.step(num, torch.stack(cat), lab)
   torch.cuda.synchronize()
   assert torch.isfinite(loss2).all() and float(loss2) != float(loss_fast)
+
+
+def test_prefetch_pipeline_matches_step():
+  """The asynchronous double-buffered input pipeline trains exactly like step()."""
+  from distributed_embeddings_b200.models.dlrm_fast import DLRMTrainStep
+  dev = torch.device("cuda", 0)
+  sizes = [100 + 7 * i for i in range(26)]
+  a = _make(3, sizes, dev)
+  b_ = _make(3, sizes, dev)
+  b_.load_state_dict(a.state_dict())
+  b_.embedding.set_weights(a.embedding.get_weights())
+  bs = 256
+  g = torch.Generator().manual_seed(9)
+  batches = []
+  for _ in range(5):
+    num = torch.rand(bs, 13, generator=g).pin_memory()
+    cat = torch.stack([torch.randint(0, s, (bs,), generator=g, dtype=torch.int32)
+                       for s in sizes]).pin_memory()
+    lab = torch.randint(0, 2, (bs,), generator=g).float().pin_memory()
+    batches.append((num, cat, lab))
+  ta = DLRMTrainStep(a, lr=0.3, use_cuda_graph=True)
+  tb = DLRMTrainStep(b_, lr=0.3, use_cuda_graph=True)
+  la = [float(ta.step(*bt)) for bt in batches]
+  lb = []
+  tb.prefetch(*batches[0])
+  for i in range(len(batches)):
+    loss = tb.run_prefetched()
+    if i + 1 < len(batches):
+      tb.prefetch(*batches[i + 1])
+    lb.append(float(loss))
+  torch.cuda.synchronize()
+  assert la == pytest.approx(lb, rel=1e-5)
+  for p, q in zip(a.dense_parameters(), b_.dense_parameters()):
+    torch.testing.assert_close(p, q, rtol=1e-4, atol=1e-5)
