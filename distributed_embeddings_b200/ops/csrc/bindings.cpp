@@ -70,14 +70,14 @@ void lookup_fwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t sr
 void scatter_add_bwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
                      int64_t grad_batch, int64_t grad_stride, at::IntArrayRef src_ptrs,
                      at::IntArrayRef grad_ptrs, int64_t rot, double scale, int64_t scale_ptr,
-                     bool ids64, bool grad_bf16, bool vec4) {
+                     bool ids64, bool grad_bf16, bool vec4, bool vec8) {
   TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
   c10::cuda::CUDAGuard guard(descs.device());
   de::launch_scatter_add_bwd(reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
                              static_cast<int>(n_inputs), batch, src_batch, grad_batch, grad_stride,
                              to_peers(src_ptrs), to_peers(grad_ptrs), static_cast<int>(rot),
                              static_cast<float>(scale), reinterpret_cast<const float*>(scale_ptr),
-                             ids64, grad_bf16, vec4, sm_count(), cur_stream());
+                             ids64, grad_bf16, vec4, sm_count(), cur_stream(), vec8);
   check_launch();
 }
 
@@ -626,7 +626,7 @@ TORCH_LIBRARY(de_b200, m) {
   m.def(
       "scatter_add_bwd(Tensor descs, int n_inputs, int batch, int src_batch, int grad_batch, "
       "int grad_stride, int[] src_ptrs, int[] grad_ptrs, int rot, float scale, int scale_ptr, bool ids64, "
-      "bool grad_bf16, bool vec4) -> ()",
+      "bool grad_bf16, bool vec4, bool vec8) -> ()",
       &scatter_add_bwd);
   m.def(
       "sort_items(Tensor descs, Tensor tables, int n_tables, int n_inputs, int batch, "

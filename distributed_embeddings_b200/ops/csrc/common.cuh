@@ -56,7 +56,12 @@ __device__ __forceinline__ FVec<VEC> ld_f32(const float* p) {
 template <int VEC>
 __device__ __forceinline__ FVec<VEC> ld_f32_rw(const float* p) {
   FVec<VEC> r;
-  if constexpr (VEC == 4) {
+  if constexpr (VEC == 8) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  } else if constexpr (VEC == 4) {
     float4 t = *reinterpret_cast<const float4*>(p);
     r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
   } else {
@@ -82,6 +87,17 @@ template <typename T, int VEC>
 __device__ __forceinline__ FVec<VEC> ld_act(const T* p) {
   if constexpr (sizeof(T) == 4) {
     return ld_f32_rw<VEC>(reinterpret_cast<const float*>(p));
+  } else if constexpr (VEC == 8) {
+    FVec<VEC> r;
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      r.v[2 * i] = f.x;
+      r.v[2 * i + 1] = f.y;
+    }
+    return r;
   } else if constexpr (VEC == 4) {
     FVec<VEC> r;
     uint2 t = *reinterpret_cast<const uint2*>(p);
@@ -118,7 +134,14 @@ __device__ __forceinline__ void st_act(T* p, const FVec<VEC>& x) {
 // Fire-and-forget vector reduction into global memory (REDG.E.ADD.F32x4 on sm_100a).
 template <int VEC>
 __device__ __forceinline__ void red_add_f32(float* p, const FVec<VEC>& x) {
-  if constexpr (VEC == 4) {
+  if constexpr (VEC == 8) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x.v[0]),
+                 "f"(x.v[1]), "f"(x.v[2]), "f"(x.v[3])
+                 : "memory");
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p + 4),
+                 "f"(x.v[4]), "f"(x.v[5]), "f"(x.v[6]), "f"(x.v[7])
+                 : "memory");
+  } else if constexpr (VEC == 4) {
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x.v[0]),
                  "f"(x.v[1]), "f"(x.v[2]), "f"(x.v[3])
                  : "memory");

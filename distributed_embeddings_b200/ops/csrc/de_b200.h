@@ -70,7 +70,7 @@ void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch,
                             int64_t grad_batch, int64_t grad_stride, const PeerPtrs& src,
                             const PeerPtrs& grad, int rot, float scale, const float* scale_ptr,
                             bool ids64, bool grad_bf16, bool vec4, int sm_count,
-                            cudaStream_t stream);
+                            cudaStream_t stream, bool vec8 = false);
 
 // ---- backward: sorted / deduplicated path -----------------------------------------------
 void launch_build_keys(const InputDesc* descs, const TableDesc* tables, int n_tables, int n_inputs,

@@ -337,9 +337,15 @@ void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch,
                             int64_t grad_batch, int64_t grad_stride, const PeerPtrs& src,
                             const PeerPtrs& grad, int rot, float scale, const float* scale_ptr,
                             bool ids64, bool grad_bf16, bool vec4, int sm_count,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, bool vec8) {
   if (n_inputs <= 0 || batch <= 0) return;
   const int grid = grid_for(count_tiles(n_inputs, batch, grad_batch), sm_count, kBlocksPerSM);
+  if (vec8 && grad_bf16) {
+    // 16-byte gradient loads: 8 columns per lane, two rows per warp instruction (peer pulls)
+    if (ids64) DE_DISPATCH_BWD(int64_t, __nv_bfloat16, 8);
+    else DE_DISPATCH_BWD(int32_t, __nv_bfloat16, 8);
+    return;
+  }
   if (vec4) {
     if (ids64) {
       if (grad_bf16) DE_DISPATCH_BWD(int64_t, __nv_bfloat16, 4);

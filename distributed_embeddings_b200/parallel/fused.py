@@ -269,6 +269,8 @@ class FusedEngine:
     cols = [int(x) for x in list(cdesc["dst_col"]) + list(ddesc["dst_col"])]
     self.vec4 = all(w % 4 == 0 for w in widths) and all(c % 4 == 0 for c in cols) and \
         tw % 4 == 0 and self.rs_width % 4 == 0
+    self.vec8 = self.vec4 and all(w % 8 == 0 for w in widths) and \
+        all(c % 8 == 0 for c in cols) and tw % 8 == 0 and not len(row_inputs)
     self._upload()
     self._key = (b, hots, ids64)
 
@@ -436,7 +438,7 @@ class FusedEngine:
       d["table"] = g.data_ptr()
       dd = _native.upload_struct_array(d, self.device)
       ops.scatter_add_bwd(dd, len(d), lb, lb, lb, self.total_width, [], [self.grad.data_ptr()], 0,
-                          1.0, 0, self.ids64, bf16, self.vec4)
+                          1.0, 0, self.ids64, bf16, self.vec4, False)
       grads.append(g)
     grads += self._backward_mp(bf16)
     return grads
@@ -470,7 +472,7 @@ class FusedEngine:
     if opt is not None and opt["kind"] == "sgd" and not opt.get("deterministic", False):
       ops.scatter_add_bwd(self._bwd_desc(), self.n_mp_inputs, B, B, lb, self.total_width, [],
                           self.grad_ptrs, self.rank, -de.mp_grad_scale, self.lr_t.data_ptr(),
-                          self.ids64, bf16, self.vec4)
+                          self.ids64, bf16, self.vec4, self.vec8 and self.W > 1)
       return [None] * n_mp
     keys, items, seg, n_unique = ops.sort_items(self._bwd_desc(), self.tdesc, n_mp,
                                                 self.n_mp_inputs, B, B, [], self.ids64,
