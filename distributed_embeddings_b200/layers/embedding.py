@@ -137,6 +137,20 @@ class Embedding(nn.Module):
       out = out.reshape(out_shape)
     return out
 
+  def regularization_loss(self) -> torch.Tensor:
+    """``embeddings_regularizer(embeddings)`` (a callable returning a scalar), 0 if unset.  Keras
+    adds this term to the loss automatically; in PyTorch the training loop adds it."""
+    if self.embeddings_regularizer is None:
+      return self.embeddings.new_zeros(())
+    return self.embeddings_regularizer(self.embeddings)
+
+  @torch.no_grad()
+  def apply_constraint(self):
+    """Project the table with ``embeddings_constraint`` (callable tensor -> tensor) in place; call
+    after the optimizer step (Keras applies constraints inside the optimizer)."""
+    if self.embeddings_constraint is not None:
+      self.embeddings.copy_(self.embeddings_constraint(self.embeddings))
+
   def get_config(self) -> Dict[str, Any]:
     return {
         "input_dim": self.input_dim,

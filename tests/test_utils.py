@@ -1,0 +1,85 @@
+"""Utilities: initializers, lr schedule, AUC, model zoo facts, regularizer/constraint hooks."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import distributed_embeddings_b200 as de
+from distributed_embeddings_b200.models import configs
+from distributed_embeddings_b200.utils import initializers
+from distributed_embeddings_b200.utils.lr_schedule import LearningRateScheduler
+from distributed_embeddings_b200.utils.metrics import binary_auc
+
+
+def test_initializers():
+  t = initializers.get("uniform")((1000, 8))
+  assert t.abs().max() <= 0.05 and t.std() > 0.01
+  d = initializers.DLRMInitializer()((400, 4))
+  assert d.abs().max() <= 1 / math.sqrt(400) + 1e-7
+  c = initializers.ConcatInitializer(initializers.DLRMInitializer(), [100, 10000])((10100, 4))
+  assert c[:100].abs().max() > c[100:].abs().max() * 3  # every member sees its own row count
+  assert torch.count_nonzero(initializers.get("zeros")((3, 3))) == 0
+  z = initializers.get({"class_name": "RandomUniform", "config": {"minval": 1.0, "maxval": 2.0}})
+  assert z((50, 2)).min() >= 1.0
+  f = initializers.get(lambda shape, dtype=None, device=None: torch.full(shape, 7.0))
+  assert f((2, 2)).eq(7).all()
+  with pytest.raises(ValueError):
+    initializers.get("nope")
+
+
+def test_lr_schedule_matches_reference_shape():
+  s = LearningRateScheduler(24.0, warmup_steps=8000, decay_start_step=48000, decay_steps=24000)
+  assert s.lr_at(0) == 0.0
+  assert s.lr_at(4000) == pytest.approx(12.0)
+  assert s.lr_at(8000) == s.lr_at(47999) == 24.0
+  assert s.lr_at(60000) == pytest.approx(24.0 * 0.25)
+  assert s.lr_at(72000) == 0.0
+  assert [s.step() for _ in range(3)] == [s.lr_at(0), s.lr_at(1), s.lr_at(2)]
+
+
+def test_auc():
+  y = torch.tensor([0, 0, 1, 1.])
+  assert binary_auc(y, torch.tensor([0.1, 0.4, 0.35, 0.8])) == pytest.approx(0.75)
+  assert binary_auc(y, torch.tensor([0.1, 0.2, 0.7, 0.8])) == 1.0
+  assert binary_auc(y, torch.tensor([0.5, 0.5, 0.5, 0.5])) == pytest.approx(0.5)
+  g = torch.Generator().manual_seed(0)
+  s = torch.rand(5000, generator=g)
+  lab = (torch.rand(5000, generator=g) < s).float()
+  # compare with a direct pair count on a subsample
+  pos, neg = s[lab > 0.5][:300], s[lab < 0.5][:300]
+  direct = ((pos[:, None] > neg[None, :]).float().mean() +
+            0.5 * (pos[:, None] == neg[None, :]).float().mean())
+  sub_y = torch.cat([torch.ones(len(pos)), torch.zeros(len(neg))])
+  assert binary_auc(sub_y, torch.cat([pos, neg])) == pytest.approx(float(direct), abs=1e-6)
+
+
+def test_model_zoo_matches_published_sizes():
+  # reference README table: tiny 55 tables / 4.2 GiB, small 107 / 26.3, large 612 / 773.8
+  facts = {"tiny": (55, 58, 4.2, 672, 85), "small": (107, 116, 26.3, 2512, 377),
+           "medium": (311, 337, 206.2, 17280, 1611), "large": (612, 669, 773.8, 36608, 6312),
+           "jumbo": (1022, 1097, 3109.5, 118400, 16022)}
+  for name, (tables, inputs, gib, width, lookups) in facts.items():
+    s = configs.summary(configs.synthetic_models_v3[name])
+    assert (s["tables"], s["inputs"], s["output_width"], s["lookups_per_sample"]) == \
+        (tables, inputs, width, lookups)
+    assert s["gib_fp32"] == pytest.approx(gib, abs=0.06)
+
+
+def test_regularizer_and_constraint_hooks():
+  e = de.Embedding(10, 4, embeddings_regularizer=lambda w: 0.5 * w.pow(2).sum(),
+                   embeddings_constraint=lambda w: w.clamp(-0.01, 0.01))
+  loss = e.regularization_loss()
+  assert loss.item() == pytest.approx(0.5 * e.embeddings.detach().pow(2).sum().item())
+  loss.backward()
+  torch.testing.assert_close(e.embeddings.grad, e.embeddings.detach())
+  e.apply_constraint()
+  assert e.embeddings.abs().max() <= 0.01 + 1e-9
+  assert de.Embedding(3, 2).regularization_loss().item() == 0.0
+
+
+def test_power_law_generator_is_skewed_and_in_range():
+  from distributed_embeddings_b200.models.synthetic import gen_power_law_data
+  ids = gen_power_law_data(20000, 3, 1000, 1.05, np.random.default_rng(0))
+  assert ids.min() >= 0 and ids.max() < 1000
+  assert (ids == 0).float().mean() > 0.05  # heavy head
