@@ -96,13 +96,16 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> sort_items(const Tensor& descs, const
                                                       int64_t n_tables, int64_t n_inputs,
                                                       int64_t batch, int64_t src_batch,
                                                       at::IntArrayRef src_ptrs, bool ids64,
-                                                      int64_t n_items, int64_t total_rows) {
+                                                      int64_t n_items, int64_t total_rows,
+                                                      bool prefill_sentinel) {
   TORCH_CHECK(descs.is_cuda() && tables.is_cuda());
   c10::cuda::CUDAGuard guard(descs.device());
   auto stream = cur_stream();
   auto i64 = at::TensorOptions().device(descs.device()).dtype(at::kLong);
   auto i32 = at::TensorOptions().device(descs.device()).dtype(at::kInt);
-  Tensor keys = at::empty({n_items}, i64), keys_sorted = at::empty({n_items}, i64);
+  // ragged inputs reserve capacity: unused slots keep the sentinel key and sort to the end
+  Tensor keys = prefill_sentinel ? at::full({n_items}, total_rows, i64) : at::empty({n_items}, i64);
+  Tensor keys_sorted = at::empty({n_items}, i64);
   Tensor items = at::empty({n_items}, i32), items_sorted = at::empty({n_items}, i32);
   Tensor seg_start = at::empty({n_items + 1}, i64);
   Tensor n_unique = at::zeros({1}, i64);
@@ -292,7 +295,7 @@ std::tuple<Tensor, Tensor> embedding_lookup_grad(const Tensor& values,
   Tensor dd = upload_bytes(&d, sizeof(d), grad.device());
   Tensor td = upload_bytes(&t, sizeof(t), grad.device());
   auto sorted = sort_items(dd, td, 1, 1, batch, batch, {}, values.scalar_type() == at::kLong,
-                           n_items, num_rows);
+                           n_items, num_rows, false);
   Tensor emit_keys = at::empty({n_items}, i64);
   Tensor emit_rows = at::empty({n_items, width}, f32);
   const bool bf16 = grad.scalar_type() == at::kBFloat16;
@@ -389,6 +392,18 @@ void gather_segments(const Tensor& segs, at::IntArrayRef src_ptrs, Tensor dst,
   de::launch_gather_segments(segs.data_ptr<int64_t>(), static_cast<int>(segs.size(0)),
                              to_peers(src_ptrs), dst.data_ptr(),
                              static_cast<int>(dst.element_size()), max_seg_elems, cur_stream());
+  check_launch();
+}
+
+void gather_ragged(const Tensor& segs, at::IntArrayRef val_ptrs, at::IntArrayRef split_ptrs,
+                   Tensor dst_vals, Tensor goff, int64_t b, int64_t max_cap) {
+  TORCH_CHECK(segs.is_cuda() && segs.scalar_type() == at::kLong && segs.is_contiguous());
+  TORCH_CHECK(goff.is_cuda() && goff.scalar_type() == at::kLong && dst_vals.is_cuda());
+  c10::cuda::CUDAGuard guard(dst_vals.device());
+  de::launch_gather_ragged(segs.data_ptr<int64_t>(), static_cast<int>(segs.size(0)),
+                           to_peers(val_ptrs), to_peers(split_ptrs), dst_vals.data_ptr(),
+                           goff.data_ptr<int64_t>(), b, static_cast<int>(val_ptrs.size()),
+                           static_cast<int>(dst_vals.element_size()), max_cap, cur_stream());
   check_launch();
 }
 
@@ -630,7 +645,8 @@ TORCH_LIBRARY(de_b200, m) {
       &scatter_add_bwd);
   m.def(
       "sort_items(Tensor descs, Tensor tables, int n_tables, int n_inputs, int batch, "
-      "int src_batch, int[] src_ptrs, bool ids64, int n_items, int total_rows) -> "
+      "int src_batch, int[] src_ptrs, bool ids64, int n_items, int total_rows, "
+      "bool prefill_sentinel) -> "
       "(Tensor, Tensor, Tensor, Tensor)",
       &sort_items);
   m.def(
@@ -670,6 +686,10 @@ TORCH_LIBRARY(de_b200, m) {
       &allreduce);
   m.def("gather_segments(Tensor segs, int[] src_ptrs, Tensor(a!) dst, int max_seg_elems) -> ()",
         &gather_segments);
+  m.def(
+      "gather_ragged(Tensor segs, int[] val_ptrs, int[] split_ptrs, Tensor(a!) dst_vals, "
+      "Tensor(b!) goff, int b, int max_cap) -> ()",
+      &gather_ragged);
   m.def("select_copy(Tensor[] src0, Tensor[] src1, Tensor(a!)[] dst, Tensor slot_flag) -> ()",
         &select_copy);
   m.def("copy_cast_2d(Tensor src, int dst_ptr, int dst_stride, bool dst_bf16, float scale) -> ()",

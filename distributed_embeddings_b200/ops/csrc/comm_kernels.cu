@@ -248,6 +248,42 @@ __global__ void select_copy_kernel(const __grid_constant__ SelectSegs segs,
   }
 }
 
+// Ragged index exchange over peer memory (replaces the reference's two hvd.alltoall calls for
+// values + row lengths and the worker-major -> feature-major transpose, dist_model_parallel.py:
+// 90-166).  Every requester stages values[cap] and row_splits[b+1] of a ragged feature in
+// symmetric buffers; the owner pulls them from all sources and builds the global-batch CSR:
+//   vals[item_off + base_s + j] = values_s[j],  goff[s*b + i] = base_s + splits_s[i],
+// with base_s = sum of the earlier sources' nnz computed on the device (no host round trip).
+// segs[j] = {src_val_off, dst_item_off, splits_off, goff_off}
+template <typename T>
+__global__ void gather_ragged_kernel(const int64_t* __restrict__ segs,
+                                     const __grid_constant__ PeerPtrs src_vals,
+                                     const __grid_constant__ PeerPtrs src_splits,
+                                     T* __restrict__ dst_vals, int64_t* __restrict__ goff,
+                                     int64_t b, int world) {
+  const int64_t* sg = segs + 4 * static_cast<int64_t>(blockIdx.y);
+  const int s = blockIdx.z;
+  __shared__ int64_t s_base, s_nnz;
+  if (threadIdx.x == 0) {
+    int64_t base = 0;
+    for (int q = 0; q < s; ++q)
+      base += (reinterpret_cast<const int64_t*>(src_splits.p[q]) + sg[2])[b];
+    s_base = base;
+    s_nnz = (reinterpret_cast<const int64_t*>(src_splits.p[s]) + sg[2])[b];
+  }
+  __syncthreads();
+  const int64_t base = s_base, nnz = s_nnz;
+  const int64_t* sp = reinterpret_cast<const int64_t*>(src_splits.p[s]) + sg[2];
+  const T* vals = reinterpret_cast<const T*>(src_vals.p[s]) + sg[0];
+  T* dv = dst_vals + sg[1] + base;
+  int64_t* go = goff + sg[3] + static_cast<int64_t>(s) * b;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (int64_t i = t0; i < nnz; i += stride) dv[i] = vals[i];
+  for (int64_t i = t0; i < b; i += stride) go[i] = base + sp[i];
+  if (s == world - 1 && t0 == 0) go[b] = base + nnz;
+}
+
 template <typename S, typename D>
 __global__ void copy_cast_2d_kernel(const S* __restrict__ src, int64_t src_stride,
                                     D* __restrict__ dst, int64_t dst_stride, int64_t rows,
@@ -332,6 +368,22 @@ void launch_select_copy(const void* const* src0, const void* const* src1, void* 
   int64_t blocks = (total + 255) / 256;
   if (blocks > sm_count * 4) blocks = sm_count * 4;
   select_copy_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(segs, slot_flag);
+}
+
+void launch_gather_ragged(const int64_t* segs, int n_seg, const PeerPtrs& src_vals,
+                          const PeerPtrs& src_splits, void* dst_vals, int64_t* goff, int64_t b,
+                          int world, int elem_bytes, int64_t max_cap, cudaStream_t stream) {
+  if (n_seg <= 0) return;
+  int64_t bx = (max_cap + 1023) / 1024;
+  if (bx > 32) bx = 32;
+  if (bx < 1) bx = 1;
+  dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(n_seg), static_cast<unsigned>(world));
+  if (elem_bytes == 8)
+    gather_ragged_kernel<int64_t><<<grid, 256, 0, stream>>>(
+        segs, src_vals, src_splits, reinterpret_cast<int64_t*>(dst_vals), goff, b, world);
+  else
+    gather_ragged_kernel<int32_t><<<grid, 256, 0, stream>>>(
+        segs, src_vals, src_splits, reinterpret_cast<int32_t*>(dst_vals), goff, b, world);
 }
 
 void launch_gather_segments(const int64_t* segs, int n_seg, const PeerPtrs& src, void* dst,

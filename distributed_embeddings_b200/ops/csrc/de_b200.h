@@ -126,6 +126,10 @@ void launch_allreduce_multimem(void* mc_ptr, const PeerPtrs& flags, uint32_t* ep
 // Segmented P2P pull: segs[j] = {src_rank, src_elem_off, dst_elem_off, n_elems}
 void launch_gather_segments(const int64_t* segs, int n_seg, const PeerPtrs& src, void* dst,
                             int elem_bytes, int64_t max_seg_elems, cudaStream_t stream);
+// Ragged P2P pull + global CSR build: segs[j] = {src_val_off, dst_item_off, splits_off, goff_off}
+void launch_gather_ragged(const int64_t* segs, int n_seg, const PeerPtrs& src_vals,
+                          const PeerPtrs& src_splits, void* dst_vals, int64_t* goff, int64_t b,
+                          int world, int elem_bytes, int64_t max_cap, cudaStream_t stream);
 // dst[i] <- (slot_flag & 1 ? src1 : src0)[i] for up to 4 segments (16-byte multiples)
 void launch_select_copy(const void* const* src0, const void* const* src1, void* const* dst,
                         const int64_t* nbytes, int count, const int* slot_flag, int sm_count,

@@ -300,17 +300,21 @@ class DistributedEmbedding(nn.Module):
         self.row_layers.append(self._create_layer(cfg, local=True))
       self.row_inputs_offsets = list(st.row_inputs_offsets[self.rank])
 
+    # native layers (incl. host-resident ones, which the kernels read zero-copy) can run fused
     self._native_layers = all(
-        isinstance(l, Embedding) and l.use_custom_kernel and not l.cpu_offloaded
+        isinstance(l, Embedding) and (l.use_custom_kernel or l.cpu_offloaded)
         for l in list(self.dp_layers) + list(self.local_embedding_layers) + list(self.row_layers))
     if backend == "auto":
       backend = "fused" if (self.device.type == "cuda" and self._native_layers) else "torch"
     if backend not in ("fused", "torch"):
       raise ValueError(f"Unsupported backend {backend}")
     if backend == "fused" and not self._native_layers:
-      raise ValueError("the fused backend needs native Embedding layers resident in HBM")
+      raise ValueError("the fused backend needs native Embedding layers")
     self.backend = backend
     self._engine = None
+    # ids-per-sample capacity reserved for ragged inputs in the fused back end (None = inferred
+    # from the first batch with 2x head room, agreed across ranks)
+    self.ragged_capacity: Optional[int] = None
     self._plan_checked = False
     self._fused_optimizer: Optional[Dict[str, Any]] = None
 

@@ -44,6 +44,16 @@ def _weight(layer):
   return layer.embeddings
 
 
+def _dev_ptr(t: torch.Tensor) -> int:
+  """Device-visible address of a tensor: CUDA tensors directly, pinned host tensors (CPU
+  offloaded tables / optimizer state) through their zero-copy UVA mapping."""
+  if t.is_cuda:
+    return t.data_ptr()
+  if not t.is_pinned():
+    raise RuntimeError("host-resident tables must live in pinned memory for the fused back end")
+  return int(_native.require().host_device_pointer(t))
+
+
 class _FusedFn(torch.autograd.Function):
 
   @staticmethod
@@ -88,11 +98,19 @@ class FusedEngine:
     # local model-parallel tables: table-parallel first, then row slices
     self.mp_layers = list(de.local_embedding_layers) + list(de.row_layers)
     self.n_col_tables = len(de.local_embedding_layers)
+    # host-resident tables are read zero-copy over PCIe; their update must not use atomics
+    self.has_offload = any(getattr(l, "cpu_offloaded", False) for l in self.mp_layers)
 
   # ------------------------------------------------------------------ capabilities
   def supports(self, inputs) -> bool:
-    for x in inputs:
-      if isinstance(x, RaggedIds) or not isinstance(x, torch.Tensor) or x.dim() > 2:
+    st, de = self.st, self.de
+    col_inputs = set(st.input_groups[1]) if de.dp_input else set(range(len(inputs)))
+    for i, x in enumerate(inputs):
+      if isinstance(x, RaggedIds):
+        if i not in col_inputs:  # ragged only for table-parallel features
+          return False
+        continue
+      if not isinstance(x, torch.Tensor) or x.dim() > 2:
         return False
     return True
 
@@ -110,11 +128,19 @@ class FusedEngine:
     col_group = st.input_groups[1] if de.dp_input else list(range(len(hots)))
     col_map = st.map_groups[1]
     # --- staging of data-parallel inputs
+    # hots[i] > 0: fixed hotness; hots[i] < 0: ragged input with capacity -hots[i] ids per sample
+    self.ragged = [h < 0 for h in hots]
+    self.any_ragged = any(self.ragged)
+    n_rag = sum(self.ragged)
+    rag_index = {}
+    for i, r in enumerate(self.ragged):
+      if r:
+        rag_index[i] = len(rag_index)
     if de.dp_input:
       in_off, pos = [], 0
       for h in hots:
         in_off.append(pos)
-        pos += b * h
+        pos += b * abs(h)
       self.in_elems = max(pos, 1)
       if W > 1:
         self.in_buf = self.ctx.alloc(self.in_elems * idsz, "ids_in")
@@ -125,27 +151,46 @@ class FusedEngine:
         in_flat = torch.zeros(self.in_elems, dtype=id_dtype, device=dev)
         self.in_ptrs = [in_flat.data_ptr()]
       self.in_flat = in_flat
-      self.in_views = [in_flat[o:o + b * h].view(b, h) for o, h in zip(in_off, hots)]
+      self.in_views = [in_flat[o:o + b * abs(h)].view(b, abs(h)) for o, h in zip(in_off, hots)]
+      # row_splits of ragged inputs (int64, [b + 1] each) live in their own symmetric buffer
+      if n_rag:
+        n_sp = n_rag * (b + 1)
+        if W > 1:
+          self.split_buf = self.ctx.alloc(n_sp * 8, "ragged_splits")
+          self.split_flat = self.split_buf.view(torch.int64, (n_sp,))
+          self.split_ptrs = self.split_buf.peer_ptrs()
+        else:
+          self.split_buf = None
+          self.split_flat = torch.zeros(n_sp, dtype=torch.int64, device=dev)
+          self.split_ptrs = [self.split_flat.data_ptr()]
+        self.split_views = {i: self.split_flat[j * (b + 1):(j + 1) * (b + 1)]
+                            for i, j in rag_index.items()}
     else:
       in_off = None
       self.in_buf, self.in_flat, self.in_views, self.in_ptrs = None, None, None, []
+      self.split_views = {}
 
     # --- model-parallel id buffer (global batch of every local input)
     my_inputs = st.input_ids_list[rank] if st.table_groups[1] else []
     col_items, pos = [], 0
     for li, k in enumerate(my_inputs):
       gi = col_group[k] if de.dp_input else li
-      h = hots[gi]
+      h = abs(hots[gi])
       col_items.append(pos)
       pos += B * h
     row_items = []
     row_inputs = st.input_groups[2] if de.dp_input else []
     for gi in row_inputs:
       row_items.append(pos)
-      pos += B * hots[gi]
+      pos += B * abs(hots[gi])
     self.n_items = pos
     need_copy = (W > 1) or (not de.dp_input)
     self.ids_mp = torch.zeros(max(pos, 1), dtype=id_dtype, device=dev) if need_copy else None
+    # global-batch CSR offsets of the ragged local inputs ([B + 1] each)
+    my_ragged = [li for li, k in enumerate(my_inputs)
+                 if self.ragged[col_group[k] if de.dp_input else li]]
+    self.goff = torch.zeros(max(len(my_ragged) * (B + 1), 1), dtype=torch.int64, device=dev)
+    goff_index = {li: j for j, li in enumerate(my_ragged)}
 
     def ids_ptr(item_off, gi):
       if need_copy:
@@ -157,7 +202,7 @@ class FusedEngine:
     key = 0
     for m, layer in enumerate(self.mp_layers):
       w = _weight(layer)
-      tdesc[m]["weight"] = w.data_ptr()
+      tdesc[m]["weight"] = _dev_ptr(w)
       tdesc[m]["rows"] = w.shape[0]
       tdesc[m]["key_base"] = key
       tdesc[m]["width"] = w.shape[1]
@@ -186,7 +231,7 @@ class FusedEngine:
     # --- table-parallel descriptors
     pieces = {(p.rank, p.local_input): p for p in st.output_pieces}
     cdesc = np.zeros(len(my_inputs), dtype=INPUT_DESC)
-    segs = []
+    segs, rsegs = [], []
     for li, k in enumerate(my_inputs):
       gi = col_group[k] if de.dp_input else li
       t_in_group = col_map[k]
@@ -194,13 +239,18 @@ class FusedEngine:
       layer = de.local_embedding_layers[shard.local_table]
       w = _weight(layer)
       d = cdesc[li]
-      d["table"] = w.data_ptr()
+      d["table"] = _dev_ptr(w)
       d["ids"] = ids_ptr(col_items[li], gi)
       d["ids_off"] = 0
       d["sub_rows"] = shard.rows
       d["row_base"] = shard.row_offset
       d["width"] = shard.width
-      d["hotness"] = hots[gi]
+      d["hotness"] = max(hots[gi], 0)
+      if self.ragged[gi]:
+        if need_copy:
+          d["offsets"] = self.goff.data_ptr() + goff_index[li] * (B + 1) * 8
+        else:  # single rank, dp input: the staged CSR is already the global one
+          d["offsets"] = self.split_views[gi].data_ptr()
       gi_global = st.input_groups[1][k]
       d["dst_col"] = self.out_cols[gi_global] + pieces[(rank, li)].col_offset
       d["combiner"] = _COMB[layer.combiner]
@@ -209,8 +259,12 @@ class FusedEngine:
       if layer.combiner is None and hots[gi] != 1:
         raise ValueError("table-parallel lookups without a combiner need one id per sample")
       if de.dp_input and W > 1:
-        for s in range(W):
-          segs.append([s, in_off[gi], col_items[li] + s * b * hots[gi], b * hots[gi]])
+        if self.ragged[gi]:
+          rsegs.append([in_off[gi], col_items[li], rag_index[gi] * (b + 1),
+                        goff_index[li] * (B + 1)])
+        else:
+          for s in range(W):
+            segs.append([s, in_off[gi], col_items[li] + s * b * hots[gi], b * hots[gi]])
     self.cdesc_np = cdesc
 
     # --- row-slice descriptors (partial pools land in rs_buf[d][slot = my rank])
@@ -265,6 +319,10 @@ class FusedEngine:
 
     self.segs = torch.tensor(segs, dtype=torch.int64, device=dev) if segs else None
     self.max_seg = max([s[3] for s in segs]) if segs else 0
+    self.rsegs = torch.tensor(rsegs, dtype=torch.int64, device=dev) if rsegs else None
+    self.max_rcap = b * max([abs(h) for h, r in zip(hots, self.ragged) if r] + [0])
+    self.my_ragged_mp = my_ragged if not de.dp_input else []
+    self.col_items = col_items
     widths = [int(x) for x in list(cdesc["width"]) + list(rdesc["width"]) + list(ddesc["width"])]
     cols = [int(x) for x in list(cdesc["dst_col"]) + list(ddesc["dst_col"])]
     self.vec4 = all(w % 4 == 0 for w in widths) and all(c % 4 == 0 for c in cols) and \
@@ -291,10 +349,10 @@ class FusedEngine:
     opt = self.de._fused_optimizer
     t = self.tdesc_np
     for m, layer in enumerate(self.mp_layers):
-      t[m]["weight"] = _weight(layer).data_ptr()
+      t[m]["weight"] = _dev_ptr(_weight(layer))
       st = self.opt_state.get(m)
-      t[m]["state0"] = st[0].data_ptr() if st else 0
-      t[m]["state1"] = st[1].data_ptr() if st and len(st) > 1 else 0
+      t[m]["state0"] = _dev_ptr(st[0]) if st else 0
+      t[m]["state1"] = _dev_ptr(st[1]) if st and len(st) > 1 else 0
     self.tdesc = _native.upload_struct_array(t, self.device) if len(t) else None
     self._tables_dirty = False
     if opt is not None:
@@ -307,15 +365,18 @@ class FusedEngine:
     if opt is None:
       return
     kind = opt["kind"]
+    def like(w, value, shape=None):
+      t = torch.full(shape or tuple(w.shape), value, dtype=torch.float32, device=w.device)
+      return t.pin_memory() if not w.is_cuda else t  # state of offloaded tables stays on the host
+
     for m, layer in enumerate(self.mp_layers):
       w = _weight(layer)
       if kind == "adagrad":
-        self.opt_state[m] = [torch.full_like(w, opt["initial_accumulator_value"])]
+        self.opt_state[m] = [like(w, opt["initial_accumulator_value"])]
       elif kind == "rowwise_adagrad":
-        self.opt_state[m] = [torch.full((w.shape[0],), opt["initial_accumulator_value"],
-                                        dtype=torch.float32, device=w.device)]
+        self.opt_state[m] = [like(w, opt["initial_accumulator_value"], (w.shape[0],))]
       elif kind == "adam":
-        self.opt_state[m] = [torch.zeros_like(w), torch.zeros_like(w)]
+        self.opt_state[m] = [like(w, 0.0), like(w, 0.0)]
     self._tables_dirty = True
 
   def update_lr(self, lr: float):
@@ -348,23 +409,57 @@ class FusedEngine:
     """``[batch, hotness]`` views of the staging buffer, one per input (dp_input mode)."""
     return self.in_views
 
+  def _ragged_capacity(self, inputs, b: int) -> int:
+    """Ids-per-sample capacity reserved for ragged inputs: user set
+    (``DistributedEmbedding.ragged_capacity``) or 2x the largest mean hotness seen at build time,
+    agreed on by all ranks (symmetric buffers must have one size)."""
+    cap = getattr(self.de, "ragged_capacity", None)
+    if cap is None:
+      need = max(int(x.values.numel()) for x in inputs if isinstance(x, RaggedIds))
+      cap = max(8, 2 * -(-need // max(b, 1)))
+      if self.W > 1:
+        t = torch.tensor([cap], dtype=torch.int64, device=self.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.de.group)
+        cap = int(t.item())
+      self.de.ragged_capacity = cap
+    return int(cap)
+
   def stage(self, inputs):
-    b = int(inputs[0].shape[0])
-    hots = tuple(1 if x.dim() == 1 else int(x.shape[1]) for x in inputs)
-    ids64 = any(x.dtype == torch.int64 for x in inputs)
+    b = inputs[0].nrows if isinstance(inputs[0], RaggedIds) else int(inputs[0].shape[0])
+    any_rag = any(isinstance(x, RaggedIds) for x in inputs)
+    cap = self._ragged_capacity(inputs, b) if any_rag else 0
+    hots = tuple(-cap if isinstance(x, RaggedIds) else (1 if x.dim() == 1 else int(x.shape[1]))
+                 for x in inputs)
+    ids64 = any((x.values if isinstance(x, RaggedIds) else x).dtype == torch.int64 for x in inputs)
     if self._key is None or self._key[0] != b or self._key[1] != hots or \
         (ids64 and not self._key[2]):
       self._build(b, hots, ids64)
     if self.de.dp_input:
-      for v, x in zip(self.in_views, inputs):
-        if x.data_ptr() != v.data_ptr():
+      for i, (v, x) in enumerate(zip(self.in_views, inputs)):
+        if isinstance(x, RaggedIds):
+          n = int(x.values.numel())
+          if n > v.numel():
+            raise ValueError(
+                f"ragged input {i} holds {n} ids but only {v.numel()} are reserved; raise "
+                "DistributedEmbedding.ragged_capacity (ids per sample) on every rank")
+          v.view(-1)[:n].copy_(x.values, non_blocking=True)
+          self.split_views[i].copy_(x.row_splits, non_blocking=True)
+        elif x.data_ptr() != v.data_ptr():
           v.copy_(x.reshape(v.shape), non_blocking=True)
     else:
-      pos = 0
-      for x in inputs:
-        n = x.numel()
-        self.ids_mp[pos:pos + n].copy_(x.reshape(-1), non_blocking=True)
-        pos += n
+      for li, x in enumerate(inputs):
+        pos = self.col_items[li]
+        if isinstance(x, RaggedIds):
+          n = int(x.values.numel())
+          if n > self.B * cap:
+            raise ValueError(f"ragged input {li} holds {n} ids, capacity is {self.B * cap}")
+          self.ids_mp[pos:pos + n].copy_(x.values, non_blocking=True)
+          j = self.my_ragged_mp.index(li)
+          self.goff[j * (self.B + 1):(j + 1) * (self.B + 1)].copy_(x.row_splits,
+                                                                     non_blocking=True)
+        else:
+          n = x.numel()
+          self.ids_mp[pos:pos + n].copy_(x.reshape(-1), non_blocking=True)
 
   def forward(self, inputs, concat: bool):
     self.stage(inputs)
@@ -397,6 +492,9 @@ class FusedEngine:
       self.ctx.barrier(0)  # every rank's ids are staged (and its partial buffer is cleared)
       if self.segs is not None:
         ops.gather_segments(self.segs, self.in_ptrs, self.ids_mp, self.max_seg)
+      if self.rsegs is not None:
+        ops.gather_ragged(self.rsegs, self.in_ptrs, self.split_ptrs, self.ids_mp, self.goff,
+                          self.lb, self.max_rcap)
     if self.ddesc is not None:
       ops.lookup_fwd(self.ddesc, len(self.ddesc_np), lb, lb, lb, self.total_width, [],
                      [self.out.data_ptr()], 0, self.ids64, bf16, self.vec4)
@@ -469,14 +567,15 @@ class FusedEngine:
     B, lb = self.B, self.lb
     # row-slice partial gradients: the gradient of an input lives in grad_buf at the input's
     # output columns for *both* groups, but row descriptors carry rs_buf columns -> patch once
-    if opt is not None and opt["kind"] == "sgd" and not opt.get("deterministic", False):
+    if opt is not None and opt["kind"] == "sgd" and not opt.get("deterministic", False) and \
+        not self.has_offload:
       ops.scatter_add_bwd(self._bwd_desc(), self.n_mp_inputs, B, B, lb, self.total_width, [],
                           self.grad_ptrs, self.rank, -de.mp_grad_scale, self.lr_t.data_ptr(),
                           self.ids64, bf16, self.vec4, self.vec8 and self.W > 1)
       return [None] * n_mp
     keys, items, seg, n_unique = ops.sort_items(self._bwd_desc(), self.tdesc, n_mp,
                                                 self.n_mp_inputs, B, B, [], self.ids64,
-                                                self.n_items, self.total_rows)
+                                                self.n_items, self.total_rows, self.any_ragged)
     if opt is not None:
       opt["step"] += 1
       t = opt["step"]
@@ -503,8 +602,8 @@ class FusedEngine:
     for m, layer in enumerate(self.mp_layers):
       w = _weight(layer)
       lo, hi = bounds[m], bounds[m + 1]
-      ids = (emit_keys[lo:hi] - bases[m]).unsqueeze(0)
-      rows = emit_rows[lo:hi, :w.shape[1]].contiguous()
+      ids = (emit_keys[lo:hi] - bases[m]).unsqueeze(0).to(w.device)
+      rows = emit_rows[lo:hi, :w.shape[1]].contiguous().to(w.device)
       out.append(torch.sparse_coo_tensor(ids, rows, size=tuple(w.shape), is_coalesced=True,
                                          check_invariants=False))
     return out

@@ -288,6 +288,16 @@ def case_ragged_dp(rank, world, device, backend, **kw):
                 ragged=True, fwd_tol=1e-6, **kw)
 
 
+def case_ragged_mean(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=31, num_tables=2 * world, hotness=5,
+                ragged=True, combiner="mean", fwd_tol=1e-6, **kw)
+
+
+def case_ragged_mp(rank, world, device, backend, **kw):
+  _generic_case(rank, world, device, backend, seed=32, num_tables=2 * world, hotness=4,
+                ragged=True, dp_input=False, fwd_tol=1e-6, **kw)
+
+
 def case_cpu_offload(rank, world, device, backend, **kw):
   sizes = 4 * [[100, 32]] + 4 * [[1000, 64]]
   test = _generic_case(rank, world, device, backend, seed=29, table_sizes=sizes, hotness=3,

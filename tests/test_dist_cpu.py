@@ -11,6 +11,7 @@ CASES = [
     "case_multihot_dp", "case_multihot_mp", "case_multihot_mean", "case_ragged_dp",
     "case_cpu_offload", "case_int32_ids", "case_dp_to_mp_input", "case_broadcast", "case_errors",
     "case_hybrid_optimizer", "case_checkpoint_resharding", "case_batch_mismatch",
+    "case_ragged_mean", "case_ragged_mp",
 ]
 
 

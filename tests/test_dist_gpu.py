@@ -10,7 +10,8 @@ FUSED_CASES = [
     "case_shared_mp", "case_mp_input", "case_column_slice_threshold",
     "case_fewer_tables_than_workers", "case_multihot_dp", "case_multihot_mp", "case_multihot_mean",
     "case_int32_ids", "case_errors", "case_hybrid_optimizer", "case_row_slice",
-    "case_data_parallel", "case_all_modes", "case_checkpoint_resharding",
+    "case_data_parallel", "case_all_modes", "case_checkpoint_resharding", "case_cpu_offload",
+    "case_ragged_dp", "case_ragged_mean", "case_ragged_mp",
 ]
 TORCH_CASES = ["case_basic", "case_ragged_dp", "case_custom_layer", "case_cpu_offload",
                "case_dp_to_mp_input", "case_broadcast"]
