@@ -51,6 +51,8 @@ def parse_args():
   p.add_argument("--gemm", default="cublas", choices=["cublas", "fused_dgrad", "tcgen05"],
                  help="MLP GEMM path of the fast trainer (see models/dlrm_fast.py)")
   p.add_argument("--profile", default=None, help="write a torch.profiler kernel table (rank 0)")
+  p.add_argument("--profile-graph", type=int, default=0,
+                 help="1 = profile CUDA-graph replays (true device timeline, no launch skew)")
   p.add_argument("--trainer", default="fast", choices=["fast", "autograd"],
                  help="fast = hand-scheduled step + CUDA graph (DLRMTrainStep); autograd = "
                       "nn.Module + HybridTrainer")
@@ -323,7 +325,7 @@ def main():
   if args.profile:
     from torch.profiler import ProfilerActivity, profile
     saved = getattr(trainer, "use_cuda_graph", None)
-    if saved is not None:
+    if saved is not None and not args.profile_graph:
       trainer.use_cuda_graph = False
     for i in range(3):
       step_from_device(i)
@@ -335,7 +337,8 @@ def main():
     if rank == 0:
       os.makedirs(os.path.dirname(args.profile) or ".", exist_ok=True)
       with open(args.profile, "w") as f:
-        f.write(f"# {args.model} world={world} global_batch={gb}, 5 eager steps (no graph)\n")
+        f.write(f"# {args.model} world={world} global_batch={gb}, 5 steps, "
+                f"{'graph replay' if args.profile_graph else 'eager (no graph)'}\n")
         f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40,
                                           max_name_column_width=70))
     if saved is not None:
@@ -381,7 +384,7 @@ def main():
             "global_batch": gb,
             "seq_len": 1,
             "parallelism": f"hybrid: dp{world} dense + table-parallel embeddings "
-                           f"(memory_balanced, column_slice_threshold={cst}), backend={args.backend}, trainer={args.trainer}, cuda_graph={int(bool(args.cuda_graph))}, mlp_gemm={args.gemm}",
+                           f"(memory_balanced, column_slice_threshold={cst}), backend={args.backend}, trainer={args.trainer}, cuda_graph={int(bool(args.cuda_graph))}, mlp_gemm={args.gemm}, dense_allreduce={getattr(trainer, 'allreduce_kind', 'torch')}",
             "optimizer": f"{args.optimizer} lr={args.lr} (embedding update fused in backward)",
             "l2_policy": "inputs larger than L2: random rows of "
                          f"{table_gb / world:.1f} GiB tables per GPU vs 126 MB L2",

@@ -100,10 +100,14 @@ class DLRMTrainStep:
     self.p32 = torch.zeros(pos, dtype=torch.float32, device=dev)
     self.p16 = torch.zeros(pos, dtype=torch.bfloat16, device=dev)
     if self.world > 1:
-      self.gsym = self.ctx.alloc(pos * 4, "dense_grads")
+      # prefer an NVSwitch multicast mapping (in-switch reduction), else plain peer mappings
+      self.gsym = self.ctx.alloc_multicast(pos * 4, "dense_grads") or \
+          self.ctx.alloc(pos * 4, "dense_grads")
+      self.allreduce_kind = "nvls_multimem" if getattr(self.gsym, "mc_ptr", 0) else "p2p"
       self.g32 = self.gsym.view(torch.float32, (pos,))
     else:
       self.gsym = None
+      self.allreduce_kind = "none"
       self.g32 = torch.zeros(pos, dtype=torch.float32, device=dev)
     # move the module parameters into the flat master buffer (strided views keep the module usable)
     with torch.no_grad():

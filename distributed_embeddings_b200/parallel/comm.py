@@ -80,6 +80,35 @@ class SymmetricBuffer:
       pass
 
 
+class MulticastBuffer:
+  """Symmetric buffer that additionally has an NVSwitch *multicast* mapping (NVLS): one
+  ``multimem.ld_reduce`` returns the sum over all GPUs computed inside the switch and one
+  ``multimem.st`` broadcasts to all of them.  Allocation and handle exchange go through
+  ``torch.distributed._symmetric_memory`` (CUDA VMM + fabric/fd handles); the kernels are ours.
+  Same surface as :class:`SymmetricBuffer` plus ``mc_ptr``."""
+
+  def __init__(self, ctx: "CommContext", nbytes: int, name: str = ""):
+    import torch.distributed._symmetric_memory as symm_mem  # pylint: disable=import-outside-toplevel
+    self.ctx, self.name = ctx, name
+    self.nbytes = (int(nbytes) + 255) // 256 * 256
+    group = ctx.group if ctx.group is not None else dist.group.WORLD
+    with torch.cuda.device(ctx.device):
+      self.local = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=ctx.device)
+      self.local.zero_()
+      self._hdl = symm_mem.rendezvous(self.local, group)
+    self.ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+    self.mc_ptr = int(self._hdl.multicast_ptr) if self._hdl.has_multicast_support else 0
+    if self.mc_ptr == 0:
+      raise RuntimeError("no multicast support")
+    torch.cuda.synchronize(ctx.device)
+
+  view = SymmetricBuffer.view
+  peer_ptrs = SymmetricBuffer.peer_ptrs
+
+  def close(self):
+    pass
+
+
 class CommContext:
   """Rank / world bookkeeping plus the device-side synchronisation state of one process group."""
 
@@ -142,6 +171,22 @@ class CommContext:
     with torch.cuda.device(self.device):
       return SymmetricBuffer(self, nbytes, name)
 
+  def alloc_multicast(self, nbytes: int, name: str = "") -> Optional[MulticastBuffer]:
+    """Symmetric buffer with an NVSwitch multicast mapping, or None when NVLS is unavailable
+    (single GPU, no NVSwitch, or the handle exchange is not permitted in this container)."""
+    if not self.p2p or self.world_size == 1 or os.environ.get("DE_B200_NVLS", "1") == "0":
+      return None
+    ok = 1
+    buf = None
+    try:
+      buf = MulticastBuffer(self, nbytes, name)
+    except Exception:  # pylint: disable=broad-except
+      ok = 0
+    # all ranks must take the same path
+    flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+    return buf if int(flag.item()) == 1 else None
+
   def barrier(self, channel: int = 0):
     """Device-side barrier on the current stream (no host synchronisation)."""
     if self.world_size == 1:
@@ -159,6 +204,10 @@ class CommContext:
       if scale != 1.0:
         buf.view(dtype, (n_elems,), byte_offset).mul_(scale)
       return
+    if mc_ptr == 0:
+      mc_ptr = getattr(buf, "mc_ptr", 0)
+      if mc_ptr:
+        mc_ptr += byte_offset
     _native.ops().allreduce(buf.peer_ptrs(byte_offset), self.signal.ptrs, self.epoch(channel),
                             self.rank, self.world_size, n_elems, float(scale),
                             dtype == torch.bfloat16, channel, self.timeout_cycles, self.error_flag,
