@@ -20,6 +20,7 @@ Same model/optimizer as the reference example (examples/dlrm/main.py:76-209): SG
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -133,6 +134,10 @@ class DLRMTrainStep:
     self._side = torch.cuda.Stream(device=dev) if overlap else None
     # weight-gradient GEMMs are off the critical path (head -> dgrads -> interaction -> embedding
     # backward): they run on a second side stream and join before the all-reduce
+    # (measured: +1.5 % at local batch 65536, but at small local batches the full-GPU cuBLAS
+    # kernels of the two streams interleave and stretch the critical chain: 0.66 -> 0.81 ms at 8
+    # GPUs, so it is only enabled for large local batches; DE_B200_WGRAD_STREAM=0/1 overrides)
+    self._wgrad_overlap = os.environ.get("DE_B200_WGRAD_STREAM", "auto")
     self._wstream = torch.cuda.Stream(device=dev) if overlap else None
 
   def _refresh_transposes(self):
@@ -151,9 +156,13 @@ class DLRMTrainStep:
 
   def _wgrad(self, L, x):
     """gw = dy^T @ x (fp32), on the weight-gradient stream."""
-    if self._wstream is None:
+    use = self._wstream is not None and (
+        self._wgrad_overlap == "1" or
+        (self._wgrad_overlap == "auto" and (self._batch or 0) >= 49152))
+    if not use:
       torch.mm(L.dy.t(), x, out_dtype=torch.float32, out=L.gw)
       return
+    self._w_used = True
     self._wstream.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(self._wstream):
       torch.mm(L.dy.t(), x, out_dtype=torch.float32, out=L.gw)
@@ -256,8 +265,9 @@ class DLRMTrainStep:
       if i > 0:
         self._dgrad_relu(L, x, self.bottom[i - 1].dy, self.bottom[i - 1].gb)
     # dense gradient all-reduce (one NVLink kernel, averaged) + fused SGD / re-cast / zero
-    if self._wstream is not None:
+    if getattr(self, "_w_used", False):  # join only a stream that took part in this step
       torch.cuda.current_stream().wait_stream(self._wstream)
+      self._w_used = False
     if self.world > 1:
       self.ctx.allreduce_(self.gsym, self.n_flat, torch.float32, scale=1.0 / self.world)
     ops.dense_sgd(self.p32, self.p16, self.g32, self.lr_t, 1.0)
