@@ -24,6 +24,7 @@ alltoall and the TF sparse optimizer kernels (reference dist_model_parallel.py:8
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -327,8 +328,12 @@ class FusedEngine:
     cols = [int(x) for x in list(cdesc["dst_col"]) + list(ddesc["dst_col"])]
     self.vec4 = all(w % 4 == 0 for w in widths) and all(c % 4 == 0 for c in cols) and \
         tw % 4 == 0 and self.rs_width % 4 == 0
-    self.vec8 = self.vec4 and all(w % 8 == 0 for w in widths) and \
-        all(c % 8 == 0 for c in cols) and tw % 8 == 0 and not len(row_inputs)
+    # 16-byte gradient pulls (8 columns per lane).  Faster in isolation (151 -> 109 us at 8 GPUs)
+    # but the whole step regressed at 4 and 8 GPUs in a same-box A/B (0.995 -> 1.11 ms at N=4), so
+    # it is opt-in until that interaction is understood: DE_B200_VEC8_PULL=1.
+    self.vec8 = os.environ.get("DE_B200_VEC8_PULL", "0") == "1" and self.vec4 and \
+        all(w % 8 == 0 for w in widths) and all(c % 8 == 0 for c in cols) and tw % 8 == 0 and \
+        not len(row_inputs)
     self._upload()
     self._key = (b, hots, ids64)
 
