@@ -197,8 +197,10 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
 
 // =============================================================================== backward
 // dst_table[row] += scale * w_sample * grad_row   (vector RED, no return value)
+// (the 8-column variant keeps 32 gradient floats per lane in flight: give it 128 registers,
+//  at 64 it spills ~440 bytes per thread)
 template <typename IdT, typename GradT, int VEC>
-__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
+__global__ void __launch_bounds__(kThreads, VEC == 8 ? 2 : kBlocksPerSM)
 scatter_add_bwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
                        int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
                        const __grid_constant__ PeerPtrs src, const __grid_constant__ PeerPtrs grad,
