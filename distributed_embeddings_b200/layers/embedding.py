@@ -5,7 +5,7 @@ Capability parity: ``distributed_embeddings/python/layers/embedding.py`` of the 
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional, Sequence, Union
+from typing import Any, Dict, List, Optional, Sequence
 
 import numpy as np
 import torch

@@ -8,7 +8,7 @@ all of them).
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import Optional
 
 
 @dataclass(frozen=True)

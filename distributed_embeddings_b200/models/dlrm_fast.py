@@ -21,7 +21,7 @@ Same model/optimizer as the reference example (examples/dlrm/main.py:76-209): SG
 from __future__ import annotations
 
 import os
-from typing import List, Optional
+from typing import Optional
 
 import torch
 from torch import nn

@@ -7,7 +7,7 @@ gradient all-reduce, optimizer apply.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence
+from typing import Callable, List, Optional
 
 import torch
 from torch import nn

@@ -81,11 +81,6 @@ __device__ __forceinline__ void grid_peer_barrier_exit(const PeerPtrs& flags, ui
 // ----------------------------------------------------------------------------- all-reduce
 // Rank r owns the r-th slice: it sums the slice over all peers (P2P loads), scales, and stores
 // the result into every peer's buffer (P2P stores).  16-byte accesses; n_vec = elements / VEC.
-template <typename T>
-struct Pack16 {
-  uint4 raw;
-};
-
 __device__ __forceinline__ void acc_f32(float (&a)[4], const uint4& v) {
   a[0] += __uint_as_float(v.x);
   a[1] += __uint_as_float(v.y);

@@ -16,7 +16,6 @@ reference (``DistributedEmbedding`` :712-1214, hybrid helpers :1217-1329).
 """
 from __future__ import annotations
 
-import math
 from typing import Any, Dict, List, Optional, Sequence, Union
 
 import numpy as np
@@ -27,7 +26,7 @@ from torch import nn
 from ..layers.embedding import Embedding, config_from_layer
 from ..ops.ragged import RaggedIds, SparseIds
 from ..utils import initializers
-from .comm import CommContext, dist_ready
+from .comm import dist_ready
 from .strategy import DistEmbeddingStrategy, STRATEGIES
 
 

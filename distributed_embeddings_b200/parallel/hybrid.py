@@ -12,7 +12,7 @@ NVLink kernel (reduce-scatter + all-gather over peer memory fused with the 1/wor
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence
+from typing import Iterable, Optional, Sequence
 
 import torch
 import torch.distributed as dist

@@ -16,7 +16,7 @@ from __future__ import annotations
 import copy
 import hashlib
 import json
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Sequence
 
 STRATEGIES = ("basic", "memory_balanced", "memory_optimized")

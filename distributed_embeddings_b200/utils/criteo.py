@@ -13,7 +13,7 @@ import math
 import os
 import queue
 import threading
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
