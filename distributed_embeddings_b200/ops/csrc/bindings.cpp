@@ -11,8 +11,10 @@
 #include <torch/library.h>
 #include <torch/torch.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -92,6 +94,56 @@ int bit_length(int64_t v) {
 
 // Build (row key, item) pairs for every looked-up id, sort by key, and find the unique rows.
 // Returns (sorted_keys, sorted_items, seg_start, n_unique[1]); nothing is copied to the host.
+// DE_B200_SORT=own routes the deduplicated update through radix_sort.cu instead of CUB
+bool use_own_sort() {
+  static const bool own = [] {
+    const char* v = std::getenv("DE_B200_SORT");
+    return v != nullptr && std::string(v) == "own";
+  }();
+  return own;
+}
+
+// standalone entry points of the first-party sort / head compaction (tests, micro-benchmarks)
+std::tuple<Tensor, Tensor> radix_sort_pairs(const Tensor& keys, const Tensor& items,
+                                            int64_t end_bit) {
+  TORCH_CHECK(keys.is_cuda() && keys.scalar_type() == at::kLong && keys.is_contiguous());
+  TORCH_CHECK(items.is_cuda() && items.scalar_type() == at::kInt && items.is_contiguous() &&
+              items.numel() == keys.numel());
+  c10::cuda::CUDAGuard guard(keys.device());
+  const int64_t n = keys.numel();
+  TORCH_CHECK(n < (int64_t(1) << 31), "own radix sort: too many items");
+  Tensor ka = keys.clone(), ia = items.clone();
+  Tensor kb = at::empty_like(ka), ib = at::empty_like(ia);
+  if (n == 0) return {ka, ia};
+  Tensor temp = at::empty({static_cast<int64_t>(de::radix_sort_temp_bytes(n))},
+                          at::TensorOptions().device(keys.device()).dtype(at::kByte));
+  int where = de::radix_sort_pairs(temp.data_ptr(), ka.data_ptr<int64_t>(),
+                                   reinterpret_cast<uint32_t*>(ia.data_ptr<int>()),
+                                   kb.data_ptr<int64_t>(),
+                                   reinterpret_cast<uint32_t*>(ib.data_ptr<int>()), n,
+                                   static_cast<int>(end_bit), cur_stream());
+  check_launch();
+  if (where == 0) return {ka, ia};
+  return {kb, ib};
+}
+
+std::tuple<Tensor, Tensor> head_segments(const Tensor& sorted_keys) {
+  TORCH_CHECK(sorted_keys.is_cuda() && sorted_keys.scalar_type() == at::kLong &&
+              sorted_keys.is_contiguous());
+  c10::cuda::CUDAGuard guard(sorted_keys.device());
+  const int64_t n = sorted_keys.numel();
+  auto i64 = at::TensorOptions().device(sorted_keys.device()).dtype(at::kLong);
+  Tensor seg_start = at::empty({n + 1}, i64);
+  Tensor n_unique = at::zeros({1}, i64);
+  if (n == 0) return {seg_start, n_unique};
+  Tensor temp = at::empty({static_cast<int64_t>(de::head_segments_temp_bytes(n))},
+                          at::TensorOptions().device(sorted_keys.device()).dtype(at::kByte));
+  de::head_segments(temp.data_ptr(), sorted_keys.data_ptr<int64_t>(), n,
+                    seg_start.data_ptr<int64_t>(), n_unique.data_ptr<int64_t>(), cur_stream());
+  check_launch();
+  return {seg_start, n_unique};
+}
+
 std::tuple<Tensor, Tensor, Tensor, Tensor> sort_items(const Tensor& descs, const Tensor& tables,
                                                       int64_t n_tables, int64_t n_inputs,
                                                       int64_t batch, int64_t src_batch,
@@ -116,6 +168,26 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> sort_items(const Tensor& descs, const
                         to_peers(src_ptrs), ids64, keys.data_ptr<int64_t>(),
                         reinterpret_cast<uint32_t*>(items.data_ptr<int>()), sm_count(), stream);
   check_launch();
+  if (use_own_sort()) {
+    TORCH_CHECK(n_items < (int64_t(1) << 31), "own radix sort: too many items");
+    size_t sort_bytes = de::radix_sort_temp_bytes(n_items);
+    size_t head_bytes = de::head_segments_temp_bytes(n_items);
+    Tensor temp = at::empty({static_cast<int64_t>(std::max(sort_bytes, head_bytes))},
+                            at::TensorOptions().device(descs.device()).dtype(at::kByte));
+    int where = de::radix_sort_pairs(temp.data_ptr(), keys.data_ptr<int64_t>(),
+                                     reinterpret_cast<uint32_t*>(items.data_ptr<int>()),
+                                     keys_sorted.data_ptr<int64_t>(),
+                                     reinterpret_cast<uint32_t*>(items_sorted.data_ptr<int>()),
+                                     n_items, bit_length(total_rows), stream);
+    if (where == 0) {
+      std::swap(keys, keys_sorted);
+      std::swap(items, items_sorted);
+    }
+    de::head_segments(temp.data_ptr(), keys_sorted.data_ptr<int64_t>(), n_items,
+                      seg_start.data_ptr<int64_t>(), n_unique.data_ptr<int64_t>(), stream);
+    check_launch();
+    return {keys_sorted, items_sorted, seg_start, n_unique};
+  }
   size_t sort_bytes = de::sort_pairs_temp_bytes(n_items);
   size_t uniq_bytes = de::unique_temp_bytes(n_items);
   Tensor temp = at::empty({static_cast<int64_t>(std::max(sort_bytes, uniq_bytes)) + 16},
@@ -649,6 +721,9 @@ TORCH_LIBRARY(de_b200, m) {
       "bool prefill_sentinel) -> "
       "(Tensor, Tensor, Tensor, Tensor)",
       &sort_items);
+  m.def("radix_sort_pairs(Tensor keys, Tensor items, int end_bit) -> (Tensor, Tensor)",
+        &radix_sort_pairs);
+  m.def("head_segments(Tensor sorted_keys) -> (Tensor, Tensor)", &head_segments);
   m.def(
       "segment_update(Tensor descs, Tensor tables, int n_tables, int batch, int grad_batch, "
       "int grad_stride, int[] grad_ptrs, Tensor sorted_keys, Tensor sorted_items, "

@@ -84,6 +84,13 @@ size_t unique_temp_bytes(int64_t n);
 // seg_start[u] = first sorted position of unique key u; *n_unique on device; seg_start[n_unique] = n
 void unique_segments(void* temp, size_t temp_bytes, const int64_t* sorted_keys, int64_t n,
                      int64_t* seg_start, int64_t* n_unique, cudaStream_t stream);
+// first-party replacements of the two CUB calls above (radix_sort.cu); DE_B200_SORT=own selects them
+size_t radix_sort_temp_bytes(int64_t n);
+int radix_sort_pairs(void* temp, int64_t* keys_a, uint32_t* items_a, int64_t* keys_b,
+                     uint32_t* items_b, int64_t n, int end_bit, cudaStream_t stream);
+size_t head_segments_temp_bytes(int64_t n);
+void head_segments(void* temp, const int64_t* sorted_keys, int64_t n, int64_t* seg_start,
+                   int64_t* n_unique, cudaStream_t stream);
 void launch_segment_update(const InputDesc* descs, const TableDesc* tables, int n_tables,
                            int64_t batch, int64_t grad_batch, int64_t grad_stride,
                            const PeerPtrs& grad, const int64_t* sorted_keys,
