@@ -375,6 +375,268 @@ gemm_tn_fused_kernel(const __grid_constant__ CUtensorMap tma_a,
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair (cta_group::2) variant
+// EXPERIMENTAL (written after the GPU budget of round 1 was spent: compiles, not yet run).
+// Two CTAs of a cluster (one TPC) cooperate on a 256 x BLOCK_N tile: CTA r stages rows
+// [r*128, r*128+128) of A and rows [r*BLOCK_N/2, ...) of B, so every operand byte is loaded once
+// per pair (half the smem fill traffic per SM); the leader CTA issues tcgen05.mma.cta_group::2
+// (UMMA 256 x BLOCK_N x 16) and each CTA's TMEM receives its 128 accumulator rows.
+//   * both producers' TMA loads (.cta_group::2) complete on the LEADER's full barrier;
+//   * tcgen05.commit ... multicast::cluster frees the smem stage / publishes the accumulator in
+//     both CTAs;
+//   * the epilogue threads of both CTAs hand the accumulator back on the leader's tmem_empty
+//     barrier (remote mbarrier.arrive through mapa).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_CL:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_CL;\n"
+      "bra WAIT_LOOP_CL;\n"
+      "DONE_CL:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map,
+                                                 uint32_t leader_bar_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_addr(smem_dst)),
+      "l"(map), "r"(leader_bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_out) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_addr(smem_out)),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the same-offset mbarrier of both CTAs once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_addr(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+template <int BLOCK_N, int STAGES>
+struct PairSmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;          // this CTA's 128 rows of A
+  static constexpr int kBBytes = (BLOCK_N / 2) * BLOCK_K * 2;    // this CTA's half of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBiasOffset = STAGES * kStageBytes;
+  static constexpr int kBarOffset = kBiasOffset + 2 * BLOCK_N * 4;
+  static constexpr int kNumBars = 2 * STAGES + 4;
+  static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16;
+};
+
+// EPI 0: C = A B^T + bias, EPI 1: relu(...)
+template <int BLOCK_N, int STAGES, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a,
+                    const __grid_constant__ CUtensorMap tma_b, const bf16* __restrict__ bias,
+                    bf16* __restrict__ C, int64_t ldc, int M, int N, int K) {
+  using L = PairSmemLayout<BLOCK_N, STAGES>;
+  constexpr int kTmemCols = 2 * BLOCK_N;
+  static_assert(kTmemCols <= 512, "two accumulators must fit the 512 TMEM columns");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOffset);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_m = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_tiles = tiles_n * tiles_m;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // the leader's expect_tx arrive (the peer's copy is unused)
+      mbar_init(&empty_bar[s], 1);  // multicast commit of the leader's MMA thread
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 256);  // epilogue threads of both CTAs (leader's copy is used)
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  } else if (warp == 1) {
+    tmem_alloc_pair<kTmemCols>(tmem_ptr_smem);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer barriers are initialised before anything signals them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / tiles_n) * (2 * BLOCK_M) + static_cast<int>(cta_rank) * BLOCK_M;
+        const int n0 = (tile % tiles_n) * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          const uint32_t leader_full = mapa_shared(smem_addr(&full_bar[stage]), 0);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          tma_load_2d_pair(sa, &tma_a, leader_full, kb * BLOCK_K, m0);
+          tma_load_2d_pair(sb, &tma_b, leader_full, kb * BLOCK_K, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_addr(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_sw128_kmajor_desc(sa + k * UMMA_K * 2);
+            const uint64_t db = make_sw128_kmajor_desc(sb + k * UMMA_K * 2);
+            umma_f16_pair(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs) =====================
+    const int quad = warp & 3;
+    const int et = (warp - 2) * 32 + lane;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int m0 = (tile / tiles_n) * (2 * BLOCK_M) + static_cast<int>(cta_rank) * BLOCK_M;
+      const int n0 = (tile % tiles_n) * BLOCK_N;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      float* sb_tile = s_bias + acc * BLOCK_N;
+      for (int i = et; i < BLOCK_N; i += 128)
+        sb_tile[i] = (bias != nullptr && n0 + i < N) ? __bfloat162float(bias[n0 + i]) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait_cluster(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      bf16* crow = C + static_cast<int64_t>(row) * ldc + n0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + c;
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] = __uint_as_float(v[j]) + sb_tile[c + j];
+          if (EPI == 1) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (row < M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (n0 + c + j < N) {
+              uint32_t packed[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+                packed[q] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(crow + c + j) =
+                  make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+          }
+        }
+      }
+      // hand the accumulator back: the leader's MMA thread waits for both CTAs' epilogues
+      tcgen05_fence_before();
+      mbar_arrive_remote(mapa_shared(smem_addr(&tmem_empty_bar[acc]), 0));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the leader's MMAs read the peer's smem: nobody leaves early
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair<kTmemCols>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------ host side: tensor maps
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                               const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -467,9 +729,47 @@ bool launch_gemm_tn_fused(const void* A, int64_t lda, const void* B, int64_t ldb
                             stream);
 }
 
+namespace {
+template <int EPI>
+bool launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const void* bias, void* C,
+                 int64_t ldc, int M, int N, int K, int sm_count, cudaStream_t stream) {
+  constexpr int BN = 256, ST = 6;
+  using L = PairSmemLayout<BN, ST>;
+  const size_t smem = L::kTotal + 1024;
+  const int tiles = ((N + BN - 1) / BN) * ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
+  int pairs = sm_count / 2;
+  if (tiles < pairs) pairs = tiles;
+  if (pairs < 1) return false;
+  cudaFuncSetAttribute(gemm_tn_pair_kernel<BN, ST, EPI>,
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  gemm_tn_pair_kernel<BN, ST, EPI><<<dim3(2 * pairs), kGemmThreads, smem, stream>>>(
+      ta, tb, reinterpret_cast<const bf16*>(bias), reinterpret_cast<bf16*>(C), ldc, M, N, K);
+  return cudaGetLastError() == cudaSuccess;
+}
+}  // namespace
+
+// CTA-pair kernel (cta_group::2, 256 x 256 tile per pair); epi 0 / 1 only.
+bool launch_gemm_tn_pair(const void* A, int64_t lda, const void* B, int64_t ldb, const void* bias,
+                         void* C, int64_t ldc, int M, int N, int K, bool relu, int sm_count,
+                         cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return true;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8) || (N % 8)) return false;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
+       reinterpret_cast<uintptr_t>(C)) & 15)
+    return false;
+  alignas(64) CUtensorMap ta, tb;
+  if (!make_tensor_map(&ta, A, M, K, lda, BLOCK_M)) return false;
+  if (!make_tensor_map(&tb, B, N, K, ldb, 128)) return false;
+  return relu ? launch_pair<1>(ta, tb, bias, C, ldc, M, N, K, sm_count, stream)
+              : launch_pair<0>(ta, tb, bias, C, ldc, M, N, K, sm_count, stream);
+}
+
 bool launch_gemm_tn_bias_act(const void* A, int64_t lda, const void* B, int64_t ldb,
                              const void* bias, void* C, int64_t ldc, int M, int N, int K,
                              bool relu, int block_n, int sm_count, cudaStream_t stream) {
+  // block_n == 512 selects the experimental CTA-pair kernel
+  if (block_n == 512)
+    return launch_gemm_tn_pair(A, lda, B, ldb, bias, C, ldc, M, N, K, relu, sm_count, stream);
   return launch_gemm_tn_fused(A, lda, B, ldb, bias, C, ldc, M, N, K, relu ? 1 : 0, nullptr, 0,
                               nullptr, block_n, sm_count, stream);
 }

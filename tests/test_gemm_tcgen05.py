@@ -58,3 +58,25 @@ def test_fused_dgrad_relu_bias(m, n, k):
   ref = (dy.float() @ w.float()) * (x > 0)
   torch.testing.assert_close(dx.float(), ref, rtol=2e-2, atol=5e-2)
   torch.testing.assert_close(colsum, ref.sum(0), rtol=2e-2, atol=0.5)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DE_B200_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="CTA-pair (cta_group::2) kernel not yet validated on hardware; "
+                    "set DE_B200_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("m,n,k", [(256, 256, 64), (512, 256, 128), (4096, 1024, 480),
+                                   (8192, 1024, 1024), (777, 512, 512), (300, 256, 256)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_gemm_cta_pair_matches_reference(m, n, k, relu):
+  """block_n=512 selects the 2-CTA kernel (UMMA 256x256x16, cta_group::2)."""
+  ops = _native.require()
+  torch.manual_seed(m + n + k)
+  a = (torch.randn(m, k, device="cuda") * 0.5).bfloat16()
+  b = (torch.randn(n, k, device="cuda") * 0.5).bfloat16()
+  bias = torch.randn(n, device="cuda").bfloat16()
+  out = torch.full((m, n), 3.0, device="cuda", dtype=torch.bfloat16)
+  ops.gemm_tn_bias_act(a, b, bias, out, relu, 512)
+  torch.cuda.synchronize()
+  ref = a.float() @ b.float().t() + bias.float()
+  if relu:
+    ref = torch.relu(ref)
+  torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2 * (k**0.5) * 0.25 + 1e-2)
