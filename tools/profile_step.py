@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel device-time breakdown of one DLRM training step (torch.profiler / CUPTI).
-Usage: python tools/profile_step.py [--model dlrm-small] [--batch 65536] [--steps 5]"""
+Usage: python tools/profile_step.py [--model dlrm-small] [--batch 65536] [--steps 5]
+       [--min-table-rows N]"""
 import argparse
 import os
 import sys
@@ -20,11 +21,14 @@ p.add_argument("--steps", type=int, default=5)
 p.add_argument("--optimizer", default="sgd")
 p.add_argument("--out", default="gpurun_out/profile_step.txt")
 p.add_argument("--trainer", default="fast")
+p.add_argument("--min-table-rows", type=int, default=0,
+               help="lift every table to at least this many rows: comparing the scatter_add kernel "
+               "time with 0 and with 1000000 isolates same-address atomic contention on tiny tables")
 args = p.parse_args()
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
-sizes = table_sizes_for(args.model)
+sizes = [max(s, args.min_table_rows) for s in table_sizes_for(args.model)]
 model = DLRM(sizes, device=dev, compute_dtype=torch.bfloat16, backend="fused")
 if args.trainer == "fast":
   from distributed_embeddings_b200.models.dlrm_fast import DLRMTrainStep

@@ -1,0 +1,25 @@
+#!/bin/bash
+# One-GPU experiment batch queued at the end of round 1 (no GPU budget was left to run it):
+#   gpurun --timeout 900 -- 'bash tools/run_round2_experiments.sh'
+# Everything lands in gpurun_out/round2/.
+set -u
+O=gpurun_out/round2; mkdir -p $O
+# 1. CTA-pair tcgen05 GEMM: correctness first (a hang here must not eat the whole call)
+DE_B200_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gemm_tcgen05.py -x -q -k cta_pair > $O/pair_gemm_test.log 2>&1
+echo "pair gemm test rc=$?" | tee -a $O/summary.txt
+if grep -q " passed" $O/pair_gemm_test.log && ! grep -q failed $O/pair_gemm_test.log; then
+  DE_B200_TEST_EXPERIMENTAL=1 timeout 120 python tools/bench_gemm.py > $O/bench_gemm_pair.log 2>&1
+fi
+# 2. own radix sort vs torch.sort (CUB) and the synthetic-small step with either sort
+timeout 200 python tools/bench_sort.py > $O/bench_sort.log 2>&1
+SYN=examples/benchmarks/synthetic_models/main.py
+for S in cub own; do
+  DE_B200_SORT=$S timeout 200 python $SYN --model small --optimizer adagrad --batch_size 65536 --alpha 1.05 \
+    --num_steps 30 --num_data_batches 2 --amp 2>&1 | grep -E '^\{' | tail -1 > $O/synth_small_sort_$S.json
+done
+# 3. same-address atomic contention of the tiny MLPerf tables in the SGD scatter kernel
+timeout 200 python tools/profile_step.py --model dlrm-mlperf --out $O/step_mlperf.txt > /dev/null 2>&1
+timeout 200 python tools/profile_step.py --model dlrm-mlperf --min-table-rows 1000000 --out $O/step_mlperf_min1m.txt > /dev/null 2>&1
+grep -h "scatter_add_bwd\|lookup_fwd" $O/step_mlperf.txt $O/step_mlperf_min1m.txt | tee -a $O/summary.txt
+# 4. headline
+timeout 300 python bench.py --steps 50 --warmup 10 | tail -1 | tee -a $O/summary.txt
