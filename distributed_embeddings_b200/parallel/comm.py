@@ -12,6 +12,7 @@ Replaces the Horovod layer of the reference (dist_model_p
 from __future__ import annotations
 
 import os
+import socket
 from typing import Dict, List, Optional
 
 import torch
@@ -26,6 +27,22 @@ NUM_CHANNELS = 16
 
 def dist_ready() -> bool:
   return dist.is_available() and dist.is_initialized()
+
+
+def host_identity() -> str:
+  """Identifies the OS instance a rank runs on (CUDA IPC handles only open inside one)."""
+  boot = ""
+  try:
+    with open("/proc/sys/kernel/random/boot_id", encoding="ascii") as f:
+      boot = f.read().strip()
+  except OSError:
+    pass
+  return f"{socket.gethostname()}/{boot}"
+
+
+def single_p2p_domain(identities: List[str], max_peers: int) -> bool:
+  """True when all ranks can map each other's memory: one host, at most ``max_peers`` ranks."""
+  return len(identities) <= max_peers and len(set(identities)) == 1
 
 
 class SymmetricBuffer:
@@ -134,10 +151,16 @@ class CommContext:
     self._epochs: Dict[int, torch.Tensor] = {}
     self.error_flag: Optional[torch.Tensor] = None
     self.timeout_cycles = DEFAULT_TIMEOUT_CYCLES
+    # Peer mappings need every rank on one host with peer access; otherwise (multi-node jobs,
+    # PCIe boxes without P2P) the context stays usable for bookkeeping and callers fall back to
+    # torch.distributed collectives (DistributedEmbedding backend "torch", NCCL all-reduce).
+    self.p2p_unavailable_reason: Optional[str] = None
     if self.is_cuda and _native.available():
-      if self.world_size > _native.MAX_PEERS:
-        raise ValueError(f"at most {_native.MAX_PEERS} ranks per P2P domain are supported")
-      self._init_p2p()
+      reason = self._p2p_obstacle()
+      if reason is None:
+        self._init_p2p()
+      else:
+        self.p2p_unavailable_reason = reason
 
   # -- construction helpers ---------------------------------------------------------------
   @classmethod
@@ -148,6 +171,25 @@ class CommContext:
                                                                 if dist_ready() else 1)):
       cls._default = CommContext(device=device)
     return cls._default
+
+  def _p2p_obstacle(self) -> Optional[str]:
+    """None when symmetric peer mappings can be set up; else why not (same answer on all ranks)."""
+    if self.world_size == 1:
+      return None
+    ids = [None] * self.world_size
+    peer_ok = True
+    me = self.device.index if self.device.index is not None else torch.cuda.current_device()
+    for d in range(torch.cuda.device_count()):
+      if d != me and not torch.cuda.can_device_access_peer(me, d):
+        peer_ok = False
+    with torch.cuda.device(self.device):  # NCCL object collectives stage through this device
+      dist.all_gather_object(ids, (host_identity(), peer_ok), group=self.group)
+    if not single_p2p_domain([i[0] for i in ids], _native.MAX_PEERS):
+      return (f"{self.world_size} ranks on {len({i[0] for i in ids})} host(s); peer mappings need "
+              f"one host and at most {_native.MAX_PEERS} ranks")
+    if not all(i[1] for i in ids):
+      return "CUDA peer access is not available between all GPUs of this host"
+    return None
 
   def _init_p2p(self):
     with torch.cuda.device(self.device):
@@ -167,7 +209,8 @@ class CommContext:
   # -- collectives --------------------------------------------------------------------------
   def alloc(self, nbytes: int, name: str = "") -> SymmetricBuffer:
     if not self.p2p:
-      raise RuntimeError("symmetric buffers need CUDA + the native extension")
+      raise RuntimeError("symmetric buffers need CUDA + the native extension" +
+                         (f" ({self.p2p_unavailable_reason})" if self.p2p_unavailable_reason else ""))
     with torch.cuda.device(self.device):
       return SymmetricBuffer(self, nbytes, name)
 

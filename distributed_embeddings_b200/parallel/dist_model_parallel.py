@@ -305,6 +305,11 @@ class DistributedEmbedding(nn.Module):
         for l in list(self.dp_layers) + list(self.local_embedding_layers) + list(self.row_layers))
     if backend == "auto":
       backend = "fused" if (self.device.type == "cuda" and self._native_layers) else "torch"
+      if backend == "fused" and self.world_size > 1 and dist_ready():
+        # multi-node jobs / GPUs without peer access: same plan, collectives through NCCL
+        from .comm import CommContext  # pylint: disable=import-outside-toplevel
+        if process_group is None and not CommContext.default(self.device).p2p:
+          backend = "torch"
     if backend not in ("fused", "torch"):
       raise ValueError(f"Unsupported backend {backend}")
     if backend == "fused" and not self._native_layers:
@@ -441,11 +446,7 @@ class DistributedEmbedding(nn.Module):
 
   def _lookup_local(self, layer, inp):
     dev = _layer_weight(layer).device
-    if isinstance(inp, RaggedIds):
-      inp = inp.to(dev)
-    else:
-      inp = inp.to(dev)
-    out = layer(inp)
+    out = layer(inp.to(dev))  # host-resident (offloaded) tables look up on the host
     return out.to(self.device)
 
   def _call_table_parallel(self, inputs):

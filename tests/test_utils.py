@@ -83,3 +83,14 @@ def test_power_law_generator_is_skewed_and_in_range():
   ids = gen_power_law_data(20000, 3, 1000, 1.05, np.random.default_rng(0))
   assert ids.min() >= 0 and ids.max() < 1000
   assert (ids == 0).float().mean() > 0.05  # heavy head
+
+
+def test_p2p_domain_detection():
+  from distributed_embeddings_b200.parallel.comm import CommContext, host_identity, single_p2p_domain
+  me = host_identity()
+  assert me == host_identity() and "/" in me
+  assert single_p2p_domain([me] * 8, 16)
+  assert not single_p2p_domain([me] * 4 + ["other-host/1"] * 4, 16)   # two nodes
+  assert not single_p2p_domain([me] * 32, 16)                         # more ranks than peer slots
+  ctx = CommContext(device="cpu")
+  assert not ctx.p2p and ctx.world_size == 1 and ctx.p2p_unavailable_reason is None
