@@ -50,6 +50,8 @@ def parse_args():
   p.add_argument("--gemm", default="cublas", choices=["cublas", "fused_dgrad", "tcgen05"],
                  help="MLP GEMM path of the fast trainer (see models/dlrm_fast.py)")
   p.add_argument("--profile", default=None, help="write a torch.profiler kernel table (rank 0)")
+  p.add_argument("--profile-all-ranks", action="store_true",
+                 help="with --profile: every rank writes its kernel table and a chrome trace")
   p.add_argument("--profile-graph", type=int, default=0,
                  help="1 = profile CUDA-graph replays (true device timeline, no launch skew)")
   p.add_argument("--trainer", default="fast", choices=["fast", "autograd"],
@@ -333,13 +335,18 @@ def main():
       for i in range(5):
         step_from_device(i)
       sync_all()
-    if rank == 0:
-      os.makedirs(os.path.dirname(args.profile) or ".", exist_ok=True)
-      with open(args.profile, "w") as f:
-        f.write(f"# {args.model} world={world} global_batch={gb}, 5 steps, "
+    if rank == 0 or args.profile_all_ranks:
+      # rank 0 -> the given path, other ranks -> path.rankN (the per-rank tables and traces are
+      # what shows which rank the barriers / all-reduce are waiting for)
+      path = args.profile if rank == 0 else f"{args.profile}.rank{rank}"
+      os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+      with open(path, "w") as f:
+        f.write(f"# {args.model} world={world} rank={rank} global_batch={gb}, 5 steps, "
                 f"{'graph replay' if args.profile_graph else 'eager (no graph)'}\n")
         f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40,
                                           max_name_column_width=70))
+      if args.profile_all_ranks:
+        prof.export_chrome_trace(f"{path}.trace.json")
     if saved is not None:
       trainer.use_cuda_graph = saved
 
