@@ -23,3 +23,9 @@ timeout 200 python tools/profile_step.py --model dlrm-mlperf --min-table-rows 10
 grep -h "scatter_add_bwd\|lookup_fwd" $O/step_mlperf.txt $O/step_mlperf_min1m.txt | tee -a $O/summary.txt
 # 4. headline
 timeout 300 python bench.py --steps 50 --warmup 10 | tail -1 | tee -a $O/summary.txt
+
+# 5. (multi-GPU, separate call) cross-rank timeline of graph replays, e.g. with gpurun --gpus 8:
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29650 \
+#     bench.py --gpus 8 --steps 20 --warmup 5 --no-e2e --profile gpurun_out/round2/prof_n8.txt \
+#     --profile-all-ranks --profile-graph 1
+#   python tools/critical_path.py gpurun_out/round2/prof_n8.txt --step 2 > gpurun_out/round2/critical_path_n8.txt
