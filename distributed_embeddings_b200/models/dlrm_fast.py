@@ -139,6 +139,13 @@ class DLRMTrainStep:
     # GPUs, so it is only enabled for large local batches; DE_B200_WGRAD_STREAM=0/1 overrides)
     self._wgrad_overlap = os.environ.get("DE_B200_WGRAD_STREAM", "auto")
     self._wstream = torch.cuda.Stream(device=dev) if overlap else None
+    # DE_B200_AR_OVERLAP=1: all-reduce the top-MLP + head gradients (93 % of the dense parameters,
+    # complete as soon as the top MLP backward is done) on a third stream while the interaction
+    # backward, the embedding exchange and the bottom MLP backward run; only the small bottom-MLP
+    # bucket is reduced at the end.  Written after the GPU budget of round 1 was spent: opt-in
+    # until the 2-GPU numerics test has run with it.
+    self._ar_stream = torch.cuda.Stream(device=dev) if (
+        overlap and self.world > 1 and os.environ.get("DE_B200_AR_OVERLAP", "0") == "1") else None
 
   def _refresh_transposes(self):
     """K-major copies of W^T for the dgrad GEMMs (2.4 M elements, a few microseconds)."""
@@ -246,6 +253,15 @@ class DLRMTrainStep:
         self._dgrad_relu(L, x, dx, self.top[i - 1].gb)
       else:
         torch.mm(L.dy, L.w16, out=dx)
+    if self._ar_stream is not None:
+      ar = self._ar_stream
+      ar.wait_stream(torch.cuda.current_stream())
+      if getattr(self, "_w_used", False):
+        ar.wait_stream(self._wstream)
+      off = self.top[0].w_off  # flat layout: bottom layers | top layers | head
+      with torch.cuda.stream(ar):
+        self.ctx.allreduce_(self.gsym, self.n_flat - off, torch.float32, scale=1.0 / self.world,
+                            byte_offset=off * 4)
     # interaction backward: embedding gradient lands in the engine's (symmetric) gradient buffer
     hb = self.bottom[-1]
     ops.interact_bwd(hb.y, eng.out, self.n_emb, self.dz, hb.dy, eng.grad.data_ptr(),
@@ -269,7 +285,15 @@ class DLRMTrainStep:
       torch.cuda.current_stream().wait_stream(self._wstream)
       self._w_used = False
     if self.world > 1:
-      self.ctx.allreduce_(self.gsym, self.n_flat, torch.float32, scale=1.0 / self.world)
+      if self._ar_stream is not None:
+        # bottom-MLP bucket, behind the top bucket on the same stream (one flag channel)
+        ar = self._ar_stream
+        ar.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(ar):
+          self.ctx.allreduce_(self.gsym, self.top[0].w_off, torch.float32, scale=1.0 / self.world)
+        torch.cuda.current_stream().wait_stream(ar)
+      else:
+        self.ctx.allreduce_(self.gsym, self.n_flat, torch.float32, scale=1.0 / self.world)
     ops.dense_sgd(self.p32, self.p16, self.g32, self.lr_t, 1.0)
     self._refresh_transposes()
     if self._side is not None:

@@ -29,3 +29,7 @@ timeout 300 python bench.py --steps 50 --warmup 10 | tail -1 | tee -a $O/summary
 #     bench.py --gpus 8 --steps 20 --warmup 5 --no-e2e --profile gpurun_out/round2/prof_n8.txt \
 #     --profile-all-ranks --profile-graph 1
 #   python tools/critical_path.py gpurun_out/round2/prof_n8.txt --step 2 > gpurun_out/round2/critical_path_n8.txt
+# 6. (2 GPUs) bucketed all-reduce overlap: numerics, then A/B
+#   DE_B200_AR_OVERLAP=1 python -m pytest tests/test_dist_gpu.py -q -x -k "dlrm_fast_world2"
+#   for V in 0 1; do DE_B200_AR_OVERLAP=$V python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+#     --master-addr 127.0.0.1 --master-port 2966$V bench.py --gpus 2 --steps 50 --warmup 10 --no-e2e | tail -1; done
