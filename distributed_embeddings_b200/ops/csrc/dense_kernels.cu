@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "de_b200.h"
 
 namespace de {
@@ -249,6 +251,143 @@ interact_bwd_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
   }
 }
 
+// ---- v2 of the interaction backward (DE_B200_INTERACT_V2=1; EXPERIMENTAL, written after the
+// round-1 GPU budget was spent).  ncu of v1: 60 % of the issue stalls are long_scoreboard, 25 %
+// warps active - a warp loads a sample, waits, computes, stores, and only then touches the next
+// sample.  v2 keeps the *next* sample's features and dz row in flight (cp.async into a second
+// buffer) while the current one is multiplied and stored, and reads dz from shared memory
+// (16-byte chunks) instead of 351 scalar global loads.  8 warps/SM x 8 KB in flight each.
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kDzMax = 512;  // staged dz elements per sample (n_inter + D <= 512)
+
+template <int D>
+__device__ __forceinline__ void issue_sample(bf16* sF, int LD, bf16* sDz, const bf16* bottom,
+                                             const bf16* emb, const bf16* dz, int n_emb,
+                                             int dz_chunks, int lane) {
+  constexpr int kChunks = D / 8;
+  const int total = (n_emb + 1) * kChunks;
+#pragma unroll 4
+  for (int c = lane; c < total; c += 32) {
+    const int row = c / kChunks, ch = c - row * kChunks;
+    const bf16* src = row == 0 ? bottom + ch * 8 : emb + (row - 1) * D + ch * 8;
+    cp_async16(sF + row * LD + ch * 8, src);
+  }
+  for (int c = lane; c < dz_chunks; c += 32) cp_async16(sDz + c * 8, dz + c * 8);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWarps * 32)
+interact_bwd_v2_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
+                       const bf16* __restrict__ emb, int64_t emb_stride, int n_emb,
+                       const bf16* __restrict__ dz, int64_t dz_stride, bf16* __restrict__ dbottom,
+                       int64_t dbottom_stride, bf16* __restrict__ demb, int64_t demb_stride,
+                       float emb_grad_scale, int64_t batch) {
+  constexpr int LD = D + 8;
+  constexpr int LDG = 40;
+  constexpr int kWarpElems = 2 * kMaxFeat * LD + 2 * kDzMax + kMaxFeat * LDG;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bf16* base = reinterpret_cast<bf16*>(smem_raw) + warp * kWarpElems;
+  bf16* sDz0 = base + 2 * kMaxFeat * LD;
+  bf16* sG = sDz0 + 2 * kDzMax;
+  const int nf = n_emb + 1;
+  const int n_inter = nf * (nf - 1) / 2;
+  const int dz_chunks = (n_inter + D + 7) >> 3;
+  zero_pad_rows<D>(base, LD, n_emb, lane);
+  zero_pad_rows<D>(base + kMaxFeat * LD, LD, n_emb, lane);
+
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kWarps;
+  int64_t s = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+  int cur = 0;
+  if (s < batch)
+    issue_sample<D>(base, LD, sDz0, bottom + s * bottom_stride, emb + s * emb_stride,
+                    dz + s * dz_stride, n_emb, dz_chunks, lane);
+  cp_async_commit();
+  for (; s < batch; s += stride, cur ^= 1) {
+    const int64_t nxt = s + stride;
+    if (nxt < batch)
+      issue_sample<D>(base + (cur ^ 1) * (kMaxFeat * LD), LD, sDz0 + (cur ^ 1) * kDzMax,
+                      bottom + nxt * bottom_stride, emb + nxt * emb_stride, dz + nxt * dz_stride,
+                      n_emb, dz_chunks, lane);
+    cp_async_commit();        // possibly empty: keeps the group arithmetic uniform
+    cp_async_wait_group<1>();  // everything but the prefetch just issued has landed
+    __syncwarp();
+    const bf16* sF = base + cur * (kMaxFeat * LD);
+    const bf16* sDz = sDz0 + cur * kDzMax;
+    for (int c = lane; c < kMaxFeat * LDG / 8; c += 32)
+      reinterpret_cast<uint4*>(sG)[c] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    for (int idx = lane; idx < n_inter; idx += 32) {
+      int i = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * idx)) * 0.5f);
+      while (i * (i - 1) / 2 > idx) --i;
+      while ((i + 1) * i / 2 <= idx) ++i;
+      const int j = idx - i * (i - 1) / 2;
+      const bf16 v = sDz[idx];
+      sG[i * LDG + j] = v;
+      sG[j * LDG + i] = v;
+    }
+    __syncwarp();
+    uint32_t ga[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        ldmatrix_x4(ga[mt][ks],
+                    smem_u32(sG + (mt * 16 + (lane & 15)) * LDG + ks * 16 + ((lane >> 4) << 3)));
+    const int cr = lane >> 2, cc = (lane & 3) << 1;
+    bf16* dbp = dbottom + s * dbottom_stride;
+    bf16* dep = demb + s * demb_stride;
+#pragma unroll 1
+    for (int n0 = 0; n0 < D; n0 += 32) {
+      float acc[2][4][4] = {};
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t b01[4], b23[4];
+        const int krow = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        const int ncol = n0 + ((lane >> 4) << 3);
+        ldmatrix_x4_trans(b01, smem_u32(sF + krow * LD + ncol));
+        ldmatrix_x4_trans(b23, smem_u32(sF + krow * LD + ncol + 16));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_bf16(acc[mt][0], ga[mt][ks], b01[0], b01[1]);
+          mma_bf16(acc[mt][1], ga[mt][ks], b01[2], b01[3]);
+          mma_bf16(acc[mt][2], ga[mt][ks], b23[0], b23[1]);
+          mma_bf16(acc[mt][3], ga[mt][ks], b23[2], b23[3]);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int row = mt * 16 + cr + half * 8;
+            const int col = n0 + nt * 8 + cc;
+            float v0 = acc[mt][nt][half * 2], v1 = acc[mt][nt][half * 2 + 1];
+            if (row == 0) {
+              v0 += __bfloat162float(sDz[n_inter + col]);
+              v1 += __bfloat162float(sDz[n_inter + col + 1]);
+              *reinterpret_cast<__nv_bfloat162*>(dbp + col) = __floats2bfloat162_rn(v0, v1);
+            } else if (row <= n_emb) {
+              *reinterpret_cast<__nv_bfloat162*>(dep + (row - 1) * D + col) =
+                  __floats2bfloat162_rn(v0 * emb_grad_scale, v1 * emb_grad_scale);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();  // all lanes are done with buffer `cur` before the next iteration refills it
+  }
+  cp_async_wait_group<0>();
+}
+
 // dy <- dy * (y > 0) (in place) ; db[c] += sum_rows dy   (db fp32, pre-zeroed)
 // Each thread owns 8 columns (one 16-byte vector) and keeps 4 rows in flight; partial column sums
 // are reduced across the block in shared memory, then one atomic per column per block.
@@ -463,6 +602,36 @@ bool launch_interact_bwd(const void* bottom, int64_t bottom_stride, const void* 
   int64_t blocks = (batch + kWarps - 1) / kWarps;
   const int64_t cap = static_cast<int64_t>(sm_count) * 8;
   if (blocks > cap) blocks = cap;
+  static const bool use_v2 = [] {
+    const char* v = std::getenv("DE_B200_INTERACT_V2");
+    return v != nullptr && v[0] == '1';
+  }();
+  const int nf = n_emb + 1;
+  const int dz_elems = (nf * (nf - 1) / 2 + dim + 7) / 8 * 8;
+  if (use_v2 && dz_elems <= kDzMax && dz_elems <= dz_stride && dz_stride % 8 == 0 &&
+      bottom_stride % 8 == 0 && emb_stride % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(bottom) |
+        reinterpret_cast<uintptr_t>(emb)) & 15) == 0 && (dim == 128 || dim == 64)) {
+    // two resident blocks per SM, each warp streams its samples through a double buffer
+    int64_t blocks2 = (batch + kWarps - 1) / kWarps;
+    if (blocks2 > static_cast<int64_t>(sm_count) * 2) blocks2 = static_cast<int64_t>(sm_count) * 2;
+#define DE_IBWD2(DD)                                                                             \
+  {                                                                                              \
+    const size_t smem =                                                                          \
+        kWarps * (2 * kMaxFeat * (DD + 8) + 2 * kDzMax + kMaxFeat * 40) * sizeof(bf16);          \
+    cudaFuncSetAttribute(interact_bwd_v2_kernel<DD>,                                             \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));   \
+    interact_bwd_v2_kernel<DD><<<static_cast<unsigned>(blocks2), kWarps * 32, smem, stream>>>(   \
+        reinterpret_cast<const bf16*>(bottom), bottom_stride, reinterpret_cast<const bf16*>(emb), \
+        emb_stride, n_emb, reinterpret_cast<const bf16*>(dz), dz_stride,                         \
+        reinterpret_cast<bf16*>(dbottom), dbottom_stride, reinterpret_cast<bf16*>(demb),         \
+        demb_stride, emb_grad_scale, batch);                                                     \
+    return true;                                                                                 \
+  }
+    if (dim == 128) DE_IBWD2(128)
+    if (dim == 64) DE_IBWD2(64)
+#undef DE_IBWD2
+  }
 #define DE_IBWD(DD)                                                                              \
   {                                                                                              \
     const size_t smem = kWarps * (kMaxFeat * (DD + 8) + kMaxFeat * 40) * sizeof(bf16);           \
