@@ -83,6 +83,21 @@ void scatter_add_bwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64
   check_launch();
 }
 
+void tiny_scatter_add_bwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
+                          int64_t grad_batch, int64_t grad_stride, at::IntArrayRef src_ptrs,
+                          at::IntArrayRef grad_ptrs, double scale, int64_t scale_ptr, bool ids64,
+                          bool grad_bf16, int64_t max_rows, int64_t max_width) {
+  TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
+  c10::cuda::CUDAGuard guard(descs.device());
+  bool ok = de::launch_tiny_scatter_add(
+      reinterpret_cast<const de::InputDesc*>(descs.data_ptr()), static_cast<int>(n_inputs), batch,
+      src_batch, grad_batch, grad_stride, to_peers(src_ptrs), to_peers(grad_ptrs),
+      static_cast<float>(scale), reinterpret_cast<const float*>(scale_ptr), ids64, grad_bf16,
+      static_cast<int>(max_rows), static_cast<int>(max_width), cur_stream());
+  TORCH_CHECK(ok, "tiny_scatter_add_bwd: unsupported shape or launch failure");
+  check_launch();
+}
+
 int bit_length(int64_t v) {
   int b = 0;
   while (v > 0) {
@@ -715,6 +730,11 @@ TORCH_LIBRARY(de_b200, m) {
       "int grad_stride, int[] src_ptrs, int[] grad_ptrs, int rot, float scale, int scale_ptr, bool ids64, "
       "bool grad_bf16, bool vec4, bool vec8) -> ()",
       &scatter_add_bwd);
+  m.def(
+      "tiny_scatter_add_bwd(Tensor descs, int n_inputs, int batch, int src_batch, int grad_batch, "
+      "int grad_stride, int[] src_ptrs, int[] grad_ptrs, float scale, int scale_ptr, bool ids64, "
+      "bool grad_bf16, int max_rows, int max_width) -> ()",
+      &tiny_scatter_add_bwd);
   m.def(
       "sort_items(Tensor descs, Tensor tables, int n_tables, int n_inputs, int batch, "
       "int src_batch, int[] src_ptrs, bool ids64, int n_items, int total_rows, "

@@ -72,6 +72,13 @@ void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch,
                             bool ids64, bool grad_bf16, bool vec4, int sm_count,
                             cudaStream_t stream, bool vec8 = false);
 
+// tiny one-hot tables: shared-memory pre-reduction (see lookup_kernels.cu)
+bool launch_tiny_scatter_add(const InputDesc* descs, int n_inputs, int64_t batch,
+                             int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
+                             const PeerPtrs& src, const PeerPtrs& grad, float scale,
+                             const float* scale_ptr, bool ids64, bool grad_bf16, int max_rows,
+                             int max_width, cudaStream_t stream);
+
 // ---- backward: sorted / deduplicated path -----------------------------------------------
 void launch_build_keys(const InputDesc* descs, const TableDesc* tables, int n_tables, int n_inputs,
                        int64_t batch, int64_t src_batch, const PeerPtrs& src, bool ids64, int64_t* keys,

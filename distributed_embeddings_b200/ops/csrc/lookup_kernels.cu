@@ -286,6 +286,78 @@ scatter_add_bwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_
   }
 }
 
+// ---- tiny tables (DE_B200_TINY_TABLES=1; EXPERIMENTAL, written after the round-1 GPU budget
+// was spent).  A table with a handful of rows receives `batch` reductions per step on the same
+// few L2 lines: ncu of the kernel above shows the atomic unit of the busiest L2 slice at 56 %
+// while the average slice sits at 17 %.  Here one block owns a chunk of samples of ONE tiny
+// one-hot input, accumulates the gradient rows in shared memory (fp32 smem atomics), and issues
+// one vector RED per touched row and 4 columns: chunk-size times fewer L2 atomics.
+constexpr int kTinyChunk = 2048;  // samples per block
+constexpr int kTinyUnroll = 4;
+
+template <typename IdT, typename GradT>
+__global__ void __launch_bounds__(kThreads)
+tiny_scatter_add_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
+                        int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
+                        const __grid_constant__ PeerPtrs src,
+                        const __grid_constant__ PeerPtrs grad, float scale,
+                        const float* __restrict__ scale_ptr, int n_chunks) {
+  extern __shared__ float s_acc[];  // [sub_rows][width]
+  if (scale_ptr != nullptr) scale *= *scale_ptr;
+  const int f = blockIdx.x / n_chunks;
+  const int chunk = blockIdx.x - f * n_chunks;
+  if (f >= n_inputs) return;
+  const InputDesc D = descs[f];
+  const int W = D.width;
+  const int rows = static_cast<int>(D.sub_rows);
+  for (int i = threadIdx.x; i < rows * W; i += kThreads) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const IdReader<IdT> rd = make_reader<IdT>(D, src, src_batch);
+  const int64_t g_lo = static_cast<int64_t>(chunk) * kTinyChunk;
+  const int64_t g_hi = min(batch, g_lo + kTinyChunk);
+  // warp per sample, lane per 4 columns (columns beyond 128 in further passes)
+  for (int64_t g0 = g_lo + warp; g0 < g_hi; g0 += kWarpsPerBlock * kTinyUnroll) {
+    for (int c0 = lane * 4; c0 < W; c0 += 128) {
+      FVec<4> gv[kTinyUnroll];
+      int64_t id[kTinyUnroll];
+#pragma unroll
+      for (int u = 0; u < kTinyUnroll; ++u) {
+        const int64_t g = g0 + static_cast<int64_t>(u) * kWarpsPerBlock;
+        id[u] = -1;
+        if (g < g_hi) {
+          int n;
+          const IdT* p = rd.sample(g, n);
+          id[u] = static_cast<int64_t>(p[0]) + D.id_shift;
+          const int64_t d = g / grad_batch;
+          const int64_t i = g - d * grad_batch;
+          gv[u] = ld_act<GradT, 4>(reinterpret_cast<const GradT*>(grad.p[d]) + i * grad_stride +
+                                   D.dst_col + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kTinyUnroll; ++u) {
+        if (static_cast<uint64_t>(id[u]) < static_cast<uint64_t>(rows)) {
+          float* a = s_acc + static_cast<int>(id[u]) * W + c0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) atomicAdd(a + k, gv[u].v[k] * scale);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* table = reinterpret_cast<float*>(const_cast<void*>(D.table));
+  const int nvec = W >> 2;
+  for (int i = threadIdx.x; i < rows * nvec; i += kThreads) {
+    const int r = i / nvec, c = (i - r * nvec) << 2;
+    FVec<4> v;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v.v[k] = s_acc[r * W + c + k];
+    if (v.v[0] != 0.f || v.v[1] != 0.f || v.v[2] != 0.f || v.v[3] != 0.f)
+      red_add_f32<4>(table + (D.row_base + r) * W + c, v);
+  }
+}
+
 int grid_for(int64_t total_tiles, int sm_count, int blocks_per_sm) {
   int64_t blocks = (total_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
   int64_t cap = static_cast<int64_t>(sm_count) * blocks_per_sm;
@@ -365,6 +437,35 @@ void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch,
       else DE_DISPATCH_BWD(int32_t, float, 1);
     }
   }
+}
+
+// One-hot inputs of tables with at most max_rows rows (width % 4 == 0): shared-memory
+// pre-reduction per 2048-sample chunk, then one vector RED per touched row segment.
+bool launch_tiny_scatter_add(const InputDesc* descs, int n_inputs, int64_t batch,
+                             int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
+                             const PeerPtrs& src, const PeerPtrs& grad, float scale,
+                             const float* scale_ptr, bool ids64, bool grad_bf16, int max_rows,
+                             int max_width, cudaStream_t stream) {
+  if (n_inputs <= 0 || batch <= 0) return true;
+  const size_t smem = static_cast<size_t>(max_rows) * max_width * sizeof(float);
+  if (smem > 96 * 1024 || (max_width & 3)) return false;
+  const int n_chunks = static_cast<int>((batch + kTinyChunk - 1) / kTinyChunk);
+  const unsigned grid = static_cast<unsigned>(n_inputs) * n_chunks;
+#define DE_TINY(IdT, GradT)                                                                       \
+  {                                                                                               \
+    cudaFuncSetAttribute(tiny_scatter_add_kernel<IdT, GradT>,                                     \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));    \
+    tiny_scatter_add_kernel<IdT, GradT><<<grid, kThreads, smem, stream>>>(                        \
+        descs, n_inputs, batch, src_batch, grad_batch, grad_stride, src, grad, scale, scale_ptr,  \
+        n_chunks);                                                                                \
+  }
+  if (ids64) {
+    if (grad_bf16) DE_TINY(int64_t, __nv_bfloat16) else DE_TINY(int64_t, float)
+  } else {
+    if (grad_bf16) DE_TINY(int32_t, __nv_bfloat16) else DE_TINY(int32_t, float)
+  }
+#undef DE_TINY
+  return cudaGetLastError() == cudaSuccess;
 }
 
 }  // namespace de

@@ -334,6 +334,8 @@ class FusedEngine:
     self.vec8 = os.environ.get("DE_B200_VEC8_PULL", "0") == "1" and self.vec4 and \
         all(w % 8 == 0 for w in widths) and all(c % 8 == 0 for c in cols) and tw % 8 == 0 and \
         not len(row_inputs)
+    # shared-memory pre-reduction of tiny one-hot tables in the SGD backward (experimental)
+    self.tiny_tables = os.environ.get("DE_B200_TINY_TABLES", "0") == "1"
     self._upload()
     self._key = (b, hots, ids64)
 
@@ -574,6 +576,18 @@ class FusedEngine:
     # output columns for *both* groups, but row descriptors carry rs_buf columns -> patch once
     if opt is not None and opt["kind"] == "sgd" and not opt.get("deterministic", False) and \
         not self.has_offload:
+      if self.tiny_tables and self.vec4:
+        # experimental: one-hot inputs of tables with <= 64 rows are pre-reduced in shared memory
+        main, n_main, tiny, n_tiny, t_rows, t_width = self._bwd_desc_split()
+        if n_main:
+          ops.scatter_add_bwd(main, n_main, B, B, lb, self.total_width, [], self.grad_ptrs,
+                              self.rank, -de.mp_grad_scale, self.lr_t.data_ptr(), self.ids64,
+                              bf16, self.vec4, self.vec8 and self.W > 1)
+        if n_tiny:
+          ops.tiny_scatter_add_bwd(tiny, n_tiny, B, B, lb, self.total_width, [], self.grad_ptrs,
+                                   -de.mp_grad_scale, self.lr_t.data_ptr(), self.ids64, bf16,
+                                   t_rows, t_width)
+        return [None] * n_mp
       ops.scatter_add_bwd(self._bwd_desc(), self.n_mp_inputs, B, B, lb, self.total_width, [],
                           self.grad_ptrs, self.rank, -de.mp_grad_scale, self.lr_t.data_ptr(),
                           self.ids64, bf16, self.vec4, self.vec8 and self.W > 1)
@@ -625,6 +639,24 @@ class FusedEngine:
       self._scratch = torch.zeros(need, dtype=torch.float32, device=self.device)
     return self._scratch
 
+  def _bwd_desc_split(self):
+    """(main descs, n, tiny descs, n, max tiny rows, max tiny width): the backward descriptors
+    split into inputs served by the RED scatter kernel and one-hot inputs of tiny tables."""
+    if getattr(self, "_split_cache", None) is not None and self._split_key == self._key:
+      return self._split_cache
+    self._bwd_desc()
+    mp = self._bwd_desc_np
+    tiny = (mp["hotness"] == 1) & (mp["offsets"] == 0) & (mp["sub_rows"] <= 64) & \
+        (mp["width"] % 4 == 0) & (mp["sub_rows"] * mp["width"] * 4 <= 96 * 1024)
+    main_np, tiny_np = mp[~tiny], mp[tiny]
+    main = _native.upload_struct_array(main_np, self.device) if len(main_np) else None
+    tin = _native.upload_struct_array(tiny_np, self.device) if len(tiny_np) else None
+    t_rows = int(tiny_np["sub_rows"].max()) if len(tiny_np) else 0
+    t_width = int(tiny_np["width"].max()) if len(tiny_np) else 0
+    self._split_cache = (main, len(main_np), tin, len(tiny_np), t_rows, t_width)
+    self._split_key = self._key
+    return self._split_cache
+
   def _bwd_desc(self):
     """Backward descriptors: same as forward but row-slice inputs read their gradient at the
     input's final output columns of grad_buf."""
@@ -635,6 +667,7 @@ class FusedEngine:
     n_c = len(self.cdesc_np)
     for j, (gi, _, _) in enumerate(self.rs_cols):
       mp[n_c + j]["dst_col"] = self.out_cols[gi]
+    self._bwd_desc_np = mp
     self._bwd_desc_cache = _native.upload_struct_array(mp, self.device)
     self._bwd_key = self._key
     return self._bwd_desc_cache

@@ -21,6 +21,11 @@ done
 timeout 200 python tools/profile_step.py --model dlrm-mlperf --out $O/step_mlperf.txt > /dev/null 2>&1
 timeout 200 python tools/profile_step.py --model dlrm-mlperf --min-table-rows 1000000 --out $O/step_mlperf_min1m.txt > /dev/null 2>&1
 grep -h "scatter_add_bwd\|lookup_fwd" $O/step_mlperf.txt $O/step_mlperf_min1m.txt | tee -a $O/summary.txt
+# 3a. tiny-table shared-memory scatter: numerics, then the scatter kernel time with it
+DE_B200_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_fused_optimizers.py -x -q -k tiny > $O/tiny_test.log 2>&1
+echo "tiny tables test rc=$?" | tee -a $O/summary.txt
+DE_B200_TINY_TABLES=1 timeout 200 python tools/profile_step.py --model dlrm-mlperf --out $O/step_mlperf_tiny.txt > /dev/null 2>&1
+grep -h "scatter_add" $O/step_mlperf_tiny.txt | tee -a $O/summary.txt
 # 3b. double-buffered interaction backward: numerics, then the step with it
 DE_B200_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_dense_kernels.py -x -q -k v2 > $O/interact_v2_test.log 2>&1
 echo "interact v2 test rc=$?" | tee -a $O/summary.txt
