@@ -438,6 +438,9 @@ class DistributedEmbedding(nn.Module):
     row_in = [inputs[i] for i in st.input_groups[2]] if self.dp_input else []
     row_out = self._call_row_slice(row_in) if row_in else []
     outs = dp_out + col_out + row_out
+    if len(outs) != len(st.rev_group_ids):
+      raise RuntimeError(f"internal: {len(dp_out)}+{len(col_out)}+{len(row_out)} outputs for "
+                         f"{len(st.rev_group_ids)} inputs")
     return [outs[i] for i in st.rev_group_ids]
 
   def _call_data_parallel(self, inputs):
@@ -491,8 +494,10 @@ class DistributedEmbedding(nn.Module):
       buf = inp.new_empty((inp.shape[0] * self.world_size,) + tuple(inp.shape[1:]))
       dist.all_gather_into_tensor(buf, inp.contiguous(), group=self.group)
       gathered.append(buf)
-    gathered = [_shift_ids(inp, off) for inp, off in zip(gathered, self.row_inputs_offsets)]
-    outs = [self.row_layers[m](inp) for m, inp in zip(self.strategy.map_groups[2], gathered)]
+    # offsets are per row-sliced table; several inputs may share one (input_table_map)
+    maps = self.strategy.map_groups[2]
+    gathered = [_shift_ids(inp, self.row_inputs_offsets[m]) for m, inp in zip(maps, gathered)]
+    outs = [self.row_layers[m](inp) for m, inp in zip(maps, gathered)]
     outs = [o.to(self.compute_dtype) for o in outs]
     return [_ReduceScatterSum.apply(o, self.group, self.mp_grad_scale) for o in outs]
 

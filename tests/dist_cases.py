@@ -501,3 +501,41 @@ def case_batch_mismatch(rank, world, device, backend, **kw):
   ids = [torch.zeros(bs, dtype=torch.int64, device=device) for _ in sizes]
   with pytest.raises(ValueError, match="same batchsize"):
     model.dist_embeddings(ids)
+
+
+def case_fuzz(rank, world, device, backend, n_seeds=6, seed0=100, **kw):
+  """Randomised plans (same on every rank): strategy x thresholds x shared tables x hotness x
+  input mode, each checked forward + backward + checkpoint against the unsharded model."""
+  rejected = 0
+  for seed in range(seed0, seed0 + n_seeds):
+    rng = random.Random(seed * 7919)
+    strategy = rng.choice(["basic", "memory_balanced", "memory_optimized"])
+    num_tables = rng.randint(world, 3 * world)
+    table_sizes = [[rng.randint(4, 40), rng.choice([4, 6, 8, 12, 16])] for _ in range(num_tables)]
+    opts = {}
+    if rng.random() < 0.5:
+      opts["column_slice_threshold"] = rng.choice([40, 100, 200])
+    dp_input = rng.random() < 0.7
+    if dp_input and rng.random() < 0.4:
+      opts["data_parallel_threshold"] = rng.choice([30, 60])
+    if dp_input and rng.random() < 0.4:
+      opts["row_slice_threshold"] = rng.choice([300, 500])
+    hot = rng.choice([None, None, 1, 3])
+    ragged = hot is not None and hot > 1 and rng.random() < 0.3 and \
+        "row_slice_threshold" not in opts
+    try:
+      _generic_case(rank, world, device, backend, seed=seed, table_sizes=table_sizes,
+                    strategy=strategy, dp_input=dp_input, shared=rng.random() < 0.5, hotness=hot,
+                    ragged=ragged, combiner=rng.choice(["sum", "mean"]) if hot else None,
+                    global_batch=4 * world, fwd_tol=1e-5, bwd_tol=1e-4, **opts, **kw)
+    except ValueError as e:
+      # infeasible plans must be rejected identically on every rank
+      if "Not enough table" not in str(e):
+        raise
+      rejected += 1
+    except Exception as e:  # pylint: disable=broad-except
+      raise AssertionError(f"fuzz seed {seed}: strategy={strategy} tables={table_sizes} "
+                           f"dp_input={dp_input} hot={hot} ragged={ragged} opts={opts}: {e}") from e
+  assert rejected <= n_seeds // 2, f"{rejected} of {n_seeds} random plans were infeasible"
+  if rank == 0:
+    print(f"case_fuzz world={world}: {n_seeds - rejected} plans checked, {rejected} infeasible")

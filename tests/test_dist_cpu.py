@@ -33,3 +33,8 @@ def test_world3_uneven():
 
 def test_dp_to_mp_unbalanced():
   launch("case_dp_to_mp_input", world=2, unbalanced=True)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_fuzz_plans(world):
+  launch("case_fuzz", world=world, n_seeds=6, seed0=100 * world)

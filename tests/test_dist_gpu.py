@@ -67,3 +67,18 @@ def test_dlrm_fast_world1(optimizer):
 @pytest.mark.parametrize("optimizer", ["sgd", "adagrad", "rowwise_adagrad"])
 def test_dlrm_fast_world2(optimizer):
   launch("case_dlrm_fast_step", world=2, device_type="cuda", backend="fused", optimizer=optimizer)
+
+
+_EXPERIMENTAL = __import__("os").environ.get("DE_B200_TEST_EXPERIMENTAL", "0") == "1"
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _EXPERIMENTAL, reason="randomised plans on the fused back end: added after "
+                    "the round-1 GPU budget was spent (the CPU/gloo version runs in test_dist_cpu); "
+                    "set DE_B200_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_fuzz_plans_fused(world):
+  if torch.cuda.device_count() < world:
+    pytest.skip(f"needs {world} GPUs")
+  launch("case_fuzz", world=world, device_type="cuda", backend="fused", n_seeds=12,
+         seed0=500 * world)
