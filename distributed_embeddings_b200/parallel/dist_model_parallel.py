@@ -497,9 +497,24 @@ class DistributedEmbedding(nn.Module):
     # offsets are per row-sliced table; several inputs may share one (input_table_map)
     maps = self.strategy.map_groups[2]
     gathered = [_shift_ids(inp, self.row_inputs_offsets[m]) for m, inp in zip(maps, gathered)]
-    outs = [self.row_layers[m](inp) for m, inp in zip(maps, gathered)]
+    outs = [self._lookup_row_shard(self.row_layers[m], inp) for m, inp in zip(maps, gathered)]
     outs = [o.to(self.compute_dtype) for o in outs]
     return [_ReduceScatterSum.apply(o, self.group, self.mp_grad_scale) for o in outs]
+
+  @staticmethod
+  def _lookup_row_shard(layer, ids):
+    """Look up shifted ids in a row shard: ids of other shards fall outside [0, rows) and must
+    contribute zero.  The native layer does that itself; a user layer sees clamped ids and its
+    rows are masked afterwards (one id per sample only - pooling inside a user layer cannot be
+    masked)."""
+    if isinstance(layer, Embedding):
+      return layer(ids)
+    if ids.dim() != 1:
+      raise ValueError("row-sliced user-defined layers support one id per sample only")
+    rows = _layer_weight(layer).shape[0]
+    valid = (ids >= 0) & (ids < rows)
+    out = layer(ids.clamp(0, rows - 1))
+    return out * valid.unsqueeze(-1).to(out.dtype)
 
   # ---------------------------------------------------------------------------- fused optimizer
   def set_optimizer(self, kind: str = "sgd", lr: float = 0.01, **kwargs):

@@ -523,11 +523,18 @@ def case_fuzz(rank, world, device, backend, n_seeds=6, seed0=100, **kw):
     hot = rng.choice([None, None, 1, 3])
     ragged = hot is not None and hot > 1 and rng.random() < 0.3 and \
         "row_slice_threshold" not in opts
+    if rng.random() < 0.25:
+      opts["gpu_embedding_size"] = rng.choice([100, 300, 800])  # some tables go to host memory
+    id_dtype = rng.choice([torch.int64, torch.int32])
+    if kw.get("backend_custom_ok", True) and hot is None and rng.random() < 0.15 and \
+        backend != "fused":
+      opts["test_custom_layer"] = True
     try:
       _generic_case(rank, world, device, backend, seed=seed, table_sizes=table_sizes,
                     strategy=strategy, dp_input=dp_input, shared=rng.random() < 0.5, hotness=hot,
                     ragged=ragged, combiner=rng.choice(["sum", "mean"]) if hot else None,
-                    global_batch=4 * world, fwd_tol=1e-5, bwd_tol=1e-4, **opts, **kw)
+                    global_batch=4 * world, fwd_tol=1e-5, bwd_tol=1e-4, id_dtype=id_dtype,
+                    **opts, **kw)
     except ValueError as e:
       # infeasible plans must be rejected identically on every rank
       if "Not enough table" not in str(e):
