@@ -237,6 +237,8 @@ class IntegerLookup(nn.Module):
   map to 0 (out of vocabulary).  On the GPU the state is an open-addressed hash table in device
   memory (``table`` with interleaved key/value slots at load factor 2/3, ``count`` with per-index
   frequencies, ``next_index``); all three are buffers and checkpoint with the module.
+  The key ``-1`` is the empty-slot marker of the table (as in the reference, whose vocabulary
+  starts with ``-1``): it is never inserted and always maps to 0.
 
   Args:
     max_tokens: vocabulary size (excluding the OOV index 0).
