@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Op micro-benchmark: ragged pooled lookup forward / gradient / SGD vs torch.nn.EmbeddingBag
 (reference examples/benchmarks/benchmark.py: voc 1M, dim 128, batch 16384, hotness <= 500),
-timed with CUDA events."""
+timed with CUDA events (host clock with --device cpu, for smoke runs)."""
+import argparse
 import os
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -15,6 +17,12 @@ from distributed_embeddings_b200.ops.ragged import RaggedIds
 
 
 def timeit(fn, iters=20, warmup=5):
+  if not torch.cuda.is_available():
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(3):
+      fn()
+    return (time.perf_counter() - t0) / 3 * 1e3
   for _ in range(warmup):
     fn()
   torch.cuda.synchronize()
@@ -28,8 +36,15 @@ def timeit(fn, iters=20, warmup=5):
 
 
 def main():
-  dev = "cuda"
-  voc, dim, batch, max_hot = 1000000, 128, 16384, 500
+  p = argparse.ArgumentParser()
+  p.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
+  p.add_argument("--voc", type=int, default=1000000)
+  p.add_argument("--dim", type=int, default=128)
+  p.add_argument("--batch", type=int, default=16384)
+  p.add_argument("--max_hot", type=int, default=500)
+  args = p.parse_args()
+  dev = args.device
+  voc, dim, batch, max_hot = args.voc, args.dim, args.batch, args.max_hot
   gen = torch.Generator().manual_seed(0)
   lens = torch.randint(1, max_hot + 1, (batch,), generator=gen)
   vals = torch.randint(0, voc, (int(lens.sum()),), generator=gen)

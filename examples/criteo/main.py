@@ -66,7 +66,7 @@ def main():
     opt_s.step()
     if i % 10 == 0:
       sizes = [lk.vocabulary_size() for lk in model.lookups[:3]]
-      print(f"step {i} loss {float(loss):.4f} vocab sizes (first 3 features) {sizes}")
+      print(f"step {i} loss {loss.item():.4f} vocab sizes (first 3 features) {sizes}")
 
 
 if __name__ == "__main__":
