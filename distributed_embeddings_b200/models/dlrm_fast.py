@@ -71,7 +71,7 @@ class DLRMTrainStep:
     self.dev = self.emb.device
     self.ops = _native.require()
     self.world = self.emb.world_size
-    self.ctx = CommContext.default(self.dev)
+    self.ctx = CommContext.for_group(self.emb.group, self.dev)
     self.scheduler = scheduler
     self.use_cuda_graph = use_cuda_graph
     self.overlap = overlap

@@ -172,6 +172,20 @@ class CommContext:
       cls._default = CommContext(device=device)
     return cls._default
 
+  _by_group: Dict[int, "CommContext"] = {}
+
+  @classmethod
+  def for_group(cls, group, device=None) -> "CommContext":
+    """Context of a process (sub)group; ``None`` is the default (world) group.  Collective: all
+    members of the group must call it at the same point."""
+    if group is None:
+      return cls.default(device)
+    ctx = cls._by_group.get(id(group))
+    if ctx is None or (device is not None and torch.device(device) != ctx.device):
+      ctx = CommContext(group=group, device=device)
+      cls._by_group[id(group)] = ctx
+    return ctx
+
   def _p2p_obstacle(self) -> Optional[str]:
     """None when symmetric peer mappings can be set up; else why not (same answer on all ranks)."""
     if self.world_size == 1:

@@ -308,7 +308,7 @@ class DistributedEmbedding(nn.Module):
       if backend == "fused" and self.world_size > 1 and dist_ready():
         # multi-node jobs / GPUs without peer access: same plan, collectives through NCCL
         from .comm import CommContext  # pylint: disable=import-outside-toplevel
-        if process_group is None and not CommContext.default(self.device).p2p:
+        if not CommContext.for_group(process_group, self.device).p2p:
           backend = "torch"
     if backend not in ("fused", "torch"):
       raise ValueError(f"Unsupported backend {backend}")

@@ -78,7 +78,7 @@ class FusedEngine:
     self.W, self.rank = de.world_size, de.rank
     self.device = de.device
     self.ops = _native.require()
-    self.ctx = CommContext.default(self.device)
+    self.ctx = CommContext.for_group(de.group, self.device)
     if self.W > 1 and not self.ctx.p2p:
       raise RuntimeError("fused back end needs CUDA peer access between all ranks")
     st = self.st

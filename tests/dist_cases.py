@@ -546,3 +546,45 @@ def case_fuzz(rank, world, device, backend, n_seeds=6, seed0=100, **kw):
   assert rejected <= n_seeds // 2, f"{rejected} of {n_seeds} random plans were infeasible"
   if rank == 0:
     print(f"case_fuzz world={world}: {n_seeds - rejected} plans checked, {rejected} infeasible")
+
+
+def case_subgroups(rank, world, device, backend, **kw):
+  """Two independent model-parallel groups inside one job (process_group argument): every
+  collective of the wrapper must stay inside its group and use group ranks."""
+  assert world % 2 == 0
+  half = world // 2
+  groups = [dist.new_group(list(range(0, half))), dist.new_group(list(range(half, world)))]
+  gid = rank // half
+  group = groups[gid]
+  grank = rank - gid * half
+  rng = np.random.default_rng(1234 + gid)  # different tables / inputs per group
+  sizes = [[30, 8], [17, 4], [64, 16], [9, 8]]
+  tables = [rng.standard_normal((r, w)).astype(np.float32) for r, w in sizes]
+  embs = [de.Embedding(r, w, combiner="sum", device=device) for r, w in sizes]
+  emb = de.DistributedEmbedding(embs, strategy="memory_balanced", column_slice_threshold=100,
+                                row_slice_threshold=900, process_group=group, device=device,
+                                backend=backend)
+  assert emb.world_size == half and emb.rank == grank
+  emb.set_weights(tables)
+  lb, hot = 3, 2
+  glob = [torch.from_numpy(rng.integers(0, r, size=(lb * half, hot))).to(device) for r, _ in sizes]
+  local = [g[grank * lb:(grank + 1) * lb] for g in glob]
+  outs = emb(local)
+  for t, o in enumerate(outs):
+    ref = tables[t][local[t].cpu().numpy()].sum(1)
+    np.testing.assert_allclose(o.detach().float().cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+  # one SGD step on sum(outputs): d table[row] = -lr * (#occurrences in the group's global batch)
+  # / group size (mean-of-ranks contract for model-parallel gradients)
+  lr = 0.5
+  loss = sum(o.float().sum() for o in outs)
+  params = [p for p in emb.parameters()]
+  grads = torch.autograd.grad(loss, params, allow_unused=True)
+  with torch.no_grad():
+    for p, g in zip(params, grads):
+      if g is not None:
+        p -= lr * (g.to_dense() if g.is_sparse else g)
+  got = emb.get_weights(all_ranks=True)
+  for t, (r, w) in enumerate(sizes):
+    cnt = np.bincount(glob[t].cpu().numpy().reshape(-1), minlength=r).astype(np.float32)
+    exp = tables[t] - lr * cnt[:, None] / half
+    np.testing.assert_allclose(got[t], exp, rtol=1e-5, atol=1e-5)

@@ -38,3 +38,7 @@ def test_dp_to_mp_unbalanced():
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_fuzz_plans(world):
   launch("case_fuzz", world=world, n_seeds=6, seed0=100 * world)
+
+
+def test_independent_subgroups():
+  launch("case_subgroups", world=4)

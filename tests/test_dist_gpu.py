@@ -82,3 +82,13 @@ def test_fuzz_plans_fused(world):
     pytest.skip(f"needs {world} GPUs")
   launch("case_fuzz", world=world, device_type="cuda", backend="fused", n_seeds=12,
          seed0=500 * world)
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.skipif(not _EXPERIMENTAL, reason="fused back end on process sub-groups: added after "
+                    "the round-1 GPU budget was spent; set DE_B200_TEST_EXPERIMENTAL=1")
+def test_subgroups_fused():
+  if torch.cuda.device_count() < 4:
+    pytest.skip("needs 4 GPUs")
+  launch("case_subgroups", world=4, device_type="cuda", backend="fused")
