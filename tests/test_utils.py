@@ -94,3 +94,28 @@ def test_p2p_domain_detection():
   assert not single_p2p_domain([me] * 32, 16)                         # more ranks than peer slots
   ctx = CommContext(device="cpu")
   assert not ctx.p2p and ctx.world_size == 1 and ctx.p2p_unavailable_reason is None
+
+
+def test_model_zoo_details():
+  """Table counts and fp32 sizes of the synthetic zoo as published by the reference
+  (examples/benchmarks/synthetic_models/README.md:11-16; config_v3.py:46-92)."""
+  from distributed_embeddings_b200.models.configs import expand, scaled, summary, synthetic_models_v3
+  published = {"tiny": (55, 4.2), "small": (107, 26.3), "medium": (311, 206.2),
+               "large": (612, 773.8), "jumbo": (1022, 3109.5), "colossal": (2002, 22327.4)}
+  for name, (tables, gib) in published.items():
+    s = summary(synthetic_models_v3[name])
+    assert s["tables"] == tables
+    assert round(s["gib_fp32"], 1) == gib
+  small = summary(synthetic_models_v3["small"])
+  assert (small["inputs"], small["elements"], small["output_width"],
+          small["lookups_per_sample"]) == (116, 7058084800, 2512, 377)
+  large = summary(synthetic_models_v3["large"])
+  assert (large["inputs"], large["output_width"], large["lookups_per_sample"]) == (669, 36608, 6312)
+  crit = summary(synthetic_models_v3["criteo"])
+  assert (crit["tables"], crit["rows"], crit["output_width"]) == (26, 2600000, 3328)
+  # scaling shrinks rows only; expand() yields one entry per table / input
+  tiny = scaled(synthetic_models_v3["tiny"], 0.001)
+  st = summary(tiny)
+  assert st["tables"] == 55 and st["output_width"] == 672 and st["rows"] < 100000
+  tables, imap, hots = expand(tiny)[:3]
+  assert len(tables) == 55 and len(imap) == 58 and len(hots) == 58
