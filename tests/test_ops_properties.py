@@ -85,3 +85,42 @@ def test_integer_lookup_matches_dict_model(max_tokens, batches):
   assert len(vocab) == len(model) + 1
   for k, i in model.items():
     assert vocab[i] == k
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(st.lists(st.integers(1, 5), min_size=1, max_size=4), st.integers(1, 9),
+       st.sampled_from([None, "sum", "mean"]), st.integers(0, 100))
+def test_embedding_layer_nd_inputs(shape, width, combiner, seed):
+  """N-D dense inputs: without a combiner the output is shape + (width,); with one the last
+  axis is pooled (reference embedding.py:120-147)."""
+  voc = 13
+  g = torch.Generator().manual_seed(seed)
+  layer = de.Embedding(voc, width, combiner=combiner, device="cpu")
+  ids = torch.randint(0, voc, tuple(shape), generator=g)
+  if combiner is not None and len(shape) < 2:
+    with pytest.raises(ValueError):
+      layer(ids)
+    return
+  out = layer(ids)
+  w = layer.embeddings.detach()
+  ref = w[ids]
+  if combiner == "sum":
+    ref = ref.sum(-2)
+  elif combiner == "mean":
+    ref = ref.mean(-2)
+  assert out.shape == ref.shape
+  torch.testing.assert_close(out.detach(), ref, rtol=1e-5, atol=1e-5)
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(st.lists(st.integers(1, 20), min_size=1, max_size=6), st.integers(1, 8), st.integers(1, 7),
+       st.integers(0, 100))
+def test_concat_one_hot_embedding(sizes, width, batch, seed):
+  g = torch.Generator().manual_seed(seed)
+  layer = de.ConcatOneHotEmbedding(sizes, width, device="cpu")
+  ids = torch.stack([torch.randint(0, s, (batch,), generator=g) for s in sizes], dim=1)
+  out = layer(ids)
+  assert out.shape == (batch, len(sizes), width)
+  offs = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+  ref = layer.params.detach()[ids + torch.from_numpy(offs)]
+  torch.testing.assert_close(out.detach(), ref)
