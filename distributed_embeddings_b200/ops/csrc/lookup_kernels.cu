@@ -13,6 +13,8 @@
 //
 // Capability parity: EmbeddingLookUpVariableHot / ...HotWide (reference
 // cc/kernels/embedding_lookup_kernels.cu:175-336) + the dense tf.gather/reduce path.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace de {
@@ -358,7 +360,19 @@ tiny_scatter_add_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64
   }
 }
 
+// DE_B200_EMB_BLOCKS_PER_SM=1..4 caps the resident CTAs per SM of the persistent lookup / scatter
+// grids (default 4 = the launch bound): fewer CTAs leave registers and shared memory for kernels
+// of other streams (the MLP GEMMs overlapped with the embedding exchange).
+int blocks_per_sm_cap(int compiled) {
+  static const int env = [] {
+    const char* v = std::getenv("DE_B200_EMB_BLOCKS_PER_SM");
+    return v != nullptr ? std::atoi(v) : 0;
+  }();
+  return (env >= 1 && env < compiled) ? env : compiled;
+}
+
 int grid_for(int64_t total_tiles, int sm_count, int blocks_per_sm) {
+  blocks_per_sm = blocks_per_sm_cap(blocks_per_sm);
   int64_t blocks = (total_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
   int64_t cap = static_cast<int64_t>(sm_count) * blocks_per_sm;
   if (blocks > cap) blocks = cap;

@@ -43,3 +43,7 @@ timeout 300 python bench.py --steps 50 --warmup 10 | tail -1 | tee -a $O/summary
 #   DE_B200_AR_OVERLAP=1 python -m pytest tests/test_dist_gpu.py -q -x -k "dlrm_fast_world2"
 #   for V in 0 1; do DE_B200_AR_OVERLAP=$V python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
 #     --master-addr 127.0.0.1 --master-port 2966$V bench.py --gpus 2 --steps 50 --warmup 10 --no-e2e | tail -1; done
+# 7. (4 or 8 GPUs) does the persistent scatter grid starve the overlapped GEMMs?
+#   for C in 4 2 1; do DE_B200_EMB_BLOCKS_PER_SM=$C python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+#     --master-addr 127.0.0.1 --master-port 2967$C bench.py --gpus 8 --steps 50 --warmup 10 --no-e2e | tail -1; done
+#   then the same with DE_B200_VEC8_PULL=1
