@@ -47,7 +47,7 @@ def parse_args():
   p.add_argument("--column-slice-threshold", default=None,
                  help="elements; 'auto' = balance the looked-up columns per rank (slices >= 64 wide)")
   p.add_argument("--cuda-graph", type=int, default=1)
-  p.add_argument("--gemm", default="cublas", choices=["cublas", "fused_dgrad", "tcgen05"],
+  p.add_argument("--gemm", default="cublas", choices=["cublas", "fused_dgrad", "tcgen05", "tcgen05_pair"],
                  help="MLP GEMM path of the fast trainer (see models/dlrm_fast.py)")
   p.add_argument("--profile", default=None, help="write a torch.profiler kernel table (rank 0)")
   p.add_argument("--profile-all-ranks", action="store_true",

@@ -58,11 +58,12 @@ class DLRMTrainStep:
                scheduler: Optional[LearningRateScheduler] = None, use_cuda_graph: bool = True,
                embedding_optimizer_kwargs: Optional[dict] = None, overlap: bool = True,
                gemm: str = "cublas"):
-    if gemm not in ("cublas", "fused_dgrad", "tcgen05"):
-      raise ValueError("gemm must be cublas | fused_dgrad | tcgen05")
+    if gemm not in ("cublas", "fused_dgrad", "tcgen05", "tcgen05_pair"):
+      raise ValueError("gemm must be cublas | fused_dgrad | tcgen05 | tcgen05_pair")
     # cublas: cuBLASLt everywhere.  fused_dgrad: forward/wgrad on cuBLASLt, dgrad on the
     # first-party tcgen05 kernel with the ReLU-backward mask + bias gradient fused in its epilogue.
-    # tcgen05: forward layers on the first-party kernel as well.
+    # tcgen05: forward layers on the first-party kernel as well.  tcgen05_pair: same, with the
+    # experimental CTA-pair (cta_group::2) kernel for layers at least 256 wide.
     self.gemm = gemm
     self.model = model
     self.emb = model.embedding
@@ -155,8 +156,9 @@ class DLRMTrainStep:
       L.w16T.copy_(L.w16.t())
 
   def _linear_fwd(self, L, x):
-    if self.gemm == "tcgen05":
-      self.ops.gemm_tn_bias_act(x, L.w16, L.b16, L.y, True, 0)
+    if self.gemm in ("tcgen05", "tcgen05_pair"):
+      pair = self.gemm == "tcgen05_pair" and L.out_f >= 256
+      self.ops.gemm_tn_bias_act(x, L.w16, L.b16, L.y, True, 512 if pair else 0)
     else:
       torch._addmm_activation(L.b16, x, L.w16.t(), out=L.y)
     return L.y
