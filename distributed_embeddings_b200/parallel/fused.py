@@ -72,13 +72,21 @@ class _FusedFn(torch.autograd.Function):
 
 class FusedEngine:
 
-  def __init__(self, de):
+  def __init__(self, de, dry=None):
+    """``dry``: a :class:`dry_run.DryRank` - the engine then builds its descriptors against host
+    buffers and runs them through the Python plan interpreter instead of the CUDA kernels (all
+    ranks of a plan in one process, no GPU; see ``dry_run.py``)."""
     self.de = de
     self.st = de.strategy
     self.W, self.rank = de.world_size, de.rank
     self.device = de.device
-    self.ops = _native.require()
-    self.ctx = CommContext.for_group(de.group, self.device)
+    self.dry = dry is not None
+    if self.dry:
+      self.ops, self.ctx = dry.ops, dry.ctx
+      dry.attach(self)
+    else:
+      self.ops = _native.require()
+      self.ctx = CommContext.for_group(de.group, self.device)
     if self.W > 1 and not self.ctx.p2p:
       raise RuntimeError("fused back end needs CUDA peer access between all ranks")
     st = self.st
@@ -101,6 +109,9 @@ class FusedEngine:
     self.n_col_tables = len(de.local_embedding_layers)
     # host-resident tables are read zero-copy over PCIe; their update must not use atomics
     self.has_offload = any(getattr(l, "cpu_offloaded", False) for l in self.mp_layers)
+
+  def _ptr(self, t: torch.Tensor) -> int:
+    return t.data_ptr() if self.dry else _dev_ptr(t)
 
   # ------------------------------------------------------------------ capabilities
   def supports(self, inputs) -> bool:
@@ -203,7 +214,7 @@ class FusedEngine:
     key = 0
     for m, layer in enumerate(self.mp_layers):
       w = _weight(layer)
-      tdesc[m]["weight"] = _dev_ptr(w)
+      tdesc[m]["weight"] = self._ptr(w)
       tdesc[m]["rows"] = w.shape[0]
       tdesc[m]["key_base"] = key
       tdesc[m]["width"] = w.shape[1]
@@ -240,7 +251,7 @@ class FusedEngine:
       layer = de.local_embedding_layers[shard.local_table]
       w = _weight(layer)
       d = cdesc[li]
-      d["table"] = _dev_ptr(w)
+      d["table"] = self._ptr(w)
       d["ids"] = ids_ptr(col_items[li], gi)
       d["ids_off"] = 0
       d["sub_rows"] = shard.rows
@@ -356,10 +367,10 @@ class FusedEngine:
     opt = self.de._fused_optimizer
     t = self.tdesc_np
     for m, layer in enumerate(self.mp_layers):
-      t[m]["weight"] = _dev_ptr(_weight(layer))
+      t[m]["weight"] = self._ptr(_weight(layer))
       st = self.opt_state.get(m)
-      t[m]["state0"] = _dev_ptr(st[0]) if st else 0
-      t[m]["state1"] = _dev_ptr(st[1]) if st and len(st) > 1 else 0
+      t[m]["state0"] = self._ptr(st[0]) if st else 0
+      t[m]["state1"] = self._ptr(st[1]) if st and len(st) > 1 else 0
     self.tdesc = _native.upload_struct_array(t, self.device) if len(t) else None
     self._tables_dirty = False
     if opt is not None:
@@ -374,7 +385,8 @@ class FusedEngine:
     kind = opt["kind"]
     def like(w, value, shape=None):
       t = torch.full(shape or tuple(w.shape), value, dtype=torch.float32, device=w.device)
-      return t.pin_memory() if not w.is_cuda else t  # state of offloaded tables stays on the host
+      # state of offloaded tables stays on the host (pinned, read zero-copy by the kernels)
+      return t.pin_memory() if not (w.is_cuda or self.dry) else t
 
     for m, layer in enumerate(self.mp_layers):
       w = _weight(layer)
@@ -538,6 +550,7 @@ class FusedEngine:
         grads.append(None)
         continue
       g = torch.zeros_like(w)
+      self._dp_grad_live = g  # keeps the buffer addressable for the plan interpreter (dry_run.py)
       sel = [j for j in range(len(self.ddesc_np)) if int(self.ddesc_np[j]["local_table"]) == m]
       d = self.ddesc_np[sel].copy()
       d["table"] = g.data_ptr()

@@ -1,0 +1,254 @@
+"""The fused engine's plan -> descriptor logic, exercised for every rank of a plan in one process
+on the CPU (parallel/dry_run.py): forward outputs and in-kernel optimizer updates of all ranks
+must equal an unsharded numpy model, for random plans at world sizes 1-8."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from distributed_embeddings_b200.parallel import dry_run
+
+
+def _dense_grad(p):
+  g = p.grad
+  if g is None:
+    return torch.zeros_like(p)
+  return g.to_dense() if g.is_sparse else g
+
+
+def assemble(des, get=lambda p: p.detach()):
+  """Global tables from the local shards of all ranks (what get_weights does with collectives);
+  ``get`` picks what to read from every local parameter (the weights, or their gradients)."""
+  st = des[0].strategy
+  n_tables = len(st.global_configs)
+  out = [None] * n_tables
+  n_dp = len(des[0].dp_layers)
+  for j, t in enumerate(st.table_groups[0]):
+    out[t] = get(des[0].weights[j]).numpy().copy()
+  for gt, t in enumerate(st.table_groups[1]):
+    cfg = st.global_configs[t]
+    full = np.full((cfg["input_dim"], cfg["output_dim"]), np.nan, dtype=np.float32)
+    for r, shards in enumerate(st.shards):
+      n_col = len(des[r].local_embedding_layers)
+      col_w = des[r].weights[n_dp:n_dp + n_col]
+      for s in shards:
+        if s.table == gt:
+          full[:, s.col_start:s.col_end] = \
+              get(col_w[s.local_table])[s.row_offset:s.row_offset + s.rows].numpy()
+    assert not np.isnan(full).any()
+    out[t] = full
+  for gt, t in enumerate(st.table_groups[2]):
+    parts = []
+    for r in range(len(des)):
+      n_col = len(des[r].local_embedding_layers)
+      parts.append(get(des[r].weights[n_dp + n_col + gt]).numpy())
+    out[t] = np.concatenate(parts, 0)
+  return out
+
+
+def reference_step(tables, imap, glob_ids, combiners, grads, lr, world, kind, state):
+  """Unsharded model: returns outputs [global batch, width] per input and updates ``tables``
+  in place with the mean-of-ranks gradient contract (sum over the global batch / world)."""
+  outs = []
+  dense = [np.zeros_like(t) for t in tables]
+  for i, t in enumerate(imap):
+    ids = glob_ids[i]
+    if isinstance(ids, list):  # ragged: one id list per sample
+      out = np.zeros((len(ids), tables[t].shape[1]), dtype=np.float32)
+      for b, row in enumerate(ids):
+        n = len(row)
+        scale = 1.0 / n if combiners[t] == "mean" else 1.0
+        out[b] = tables[t][row].sum(0) * scale
+        np.add.at(dense[t], np.asarray(row, dtype=np.int64), grads[i][b] * scale)
+      outs.append(out)
+      continue
+    rows = tables[t][ids]  # [B, h, w]
+    n = ids.shape[1]
+    outs.append(rows.sum(1) / (n if combiners[t] == "mean" else 1))
+    g = grads[i] / (n if combiners[t] == "mean" else 1)
+    np.add.at(dense[t], ids.reshape(-1), np.repeat(g, n, axis=0))
+  if kind == "none":
+    return outs, [g / world for g in dense]
+  for t, g in enumerate(dense):
+    g = g / world
+    touched = np.abs(g).sum(1) != 0
+    if kind == "sgd":
+      tables[t] -= lr * g
+    elif kind == "adagrad":
+      acc = state.setdefault(t, np.full_like(tables[t], 0.1))
+      acc[touched] += g[touched]**2
+      tables[t][touched] -= lr * g[touched] / (np.sqrt(acc[touched]) + 1e-7)
+    elif kind == "rowwise_adagrad":
+      acc = state.setdefault(t, np.full(tables[t].shape[0], 0.1, dtype=np.float32))
+      acc[touched] += (g[touched]**2).mean(1)
+      tables[t][touched] -= lr * g[touched] / (np.sqrt(acc[touched])[:, None] + 1e-7)
+    elif kind == "adam":  # first step of lazy Adam: m/bias1 = g, v/bias2 = g^2
+      tables[t][touched] -= lr * g[touched] / (np.abs(g[touched]) + 1e-8)
+  return outs
+
+
+def run_plan(seed, world, kind="sgd", dtype=torch.float32, ragged=False):
+  rng = random.Random(seed)
+  nrng = np.random.default_rng(seed)
+  n_tables = rng.randint(max(1, world // 2), 2 * world + 2)
+  if kind == "rowwise_adagrad":
+    n_tables = max(n_tables, world)  # no automatic column slicing (see below)
+  sizes = [(rng.randint(3, 50), rng.choice([4, 8, 12, 16])) for _ in range(n_tables)]
+  combiners = [rng.choice(["sum", "mean"]) for _ in sizes]
+  imap = list(range(n_tables)) + [rng.randint(0, n_tables - 1) for _ in range(rng.randint(0, 3))]
+  rng.shuffle(imap)
+  if sorted(set(imap)) != list(range(n_tables)):
+    imap = list(range(n_tables))
+  hots = {t: rng.choice([1, 1, 2, 3]) for t in range(n_tables)}
+  kw = {"strategy": rng.choice(["basic", "memory_balanced", "memory_optimized"]),
+        "input_table_map": imap}
+  # a column slice keeps its own per-row accumulator (mean of g^2 over *its* columns), so the
+  # unsharded reference only applies to row-wise Adagrad when tables are not column sliced
+  if rng.random() < 0.5 and kind != "rowwise_adagrad":
+    kw["column_slice_threshold"] = rng.choice([40, 100, 250])
+  if rng.random() < 0.2:
+    kw["gpu_embedding_size"] = rng.choice([150, 400])  # some tables become "host resident"
+  dp_input = rng.random() < 0.75
+  kw["dp_input"] = dp_input
+  plain = ragged or kind == "rowwise_adagrad"  # keep every table in the table-parallel group
+  if dp_input and world > 1 and rng.random() < 0.4 and not plain:
+    kw["data_parallel_threshold"] = rng.choice([30, 80])
+  if dp_input and world > 1 and rng.random() < 0.4 and not plain:
+    kw["row_slice_threshold"] = rng.choice([300, 500])
+  embs = [{"input_dim": r, "output_dim": w, "combiner": c} for (r, w), c in zip(sizes, combiners)]
+  try:
+    sim, des = dry_run.build_engines(embs, world, compute_dtype=dtype, **kw)
+  except ValueError as e:
+    if "Not enough table" in str(e):
+      return "infeasible"
+    raise
+  tables = [nrng.standard_normal(s).astype(np.float32) for s in sizes]
+  for de in des:
+    de.set_weights(tables)
+    if kind != "none":
+      de.set_optimizer(kind, lr=0.5)
+  lb = rng.choice([2, 3, 5])
+  B = lb * world
+  glob = [nrng.integers(0, sizes[t][0], size=(B, hots[t])) for t in imap]
+  id_dtype = rng.choice([np.int64, np.int32])
+  rag = [ragged and rng.random() < 0.6 for _ in imap]
+  for i, t in enumerate(imap):
+    if rag[i]:
+      glob[i] = [list(nrng.integers(0, sizes[t][0], size=rng.randint(1, 4))) for _ in range(B)]
+  if ragged:
+    for de in des:
+      de.ragged_capacity = 4
+
+  def as_input(i, lo, hi):
+    from distributed_embeddings_b200.ops.ragged import RaggedIds
+    if rag[i]:
+      rows = glob[i][lo:hi]
+      return RaggedIds.from_row_lengths(
+          torch.tensor([v for row in rows for v in row], dtype=torch.int64),
+          torch.tensor([len(row) for row in rows], dtype=torch.int64))
+    return torch.from_numpy(glob[i][lo:hi].astype(id_dtype))
+
+  widths = [sizes[t][1] for t in imap]
+  grads = [nrng.standard_normal((B, w)).astype(np.float32) * 0.1 for w in widths]
+  st = des[0].strategy
+  dp_tables = set(st.table_groups[0])
+
+  def rank_fn(r):
+    de = des[r]
+    sl = slice(r * lb, (r + 1) * lb)
+    if dp_input:
+      inputs = [as_input(i, r * lb, (r + 1) * lb) for i in range(len(imap))]
+    else:
+      inputs = [as_input(i, 0, B) for i in st.input_ids_list[r]]
+    out = de(inputs, concat=True)
+    assert de._engine.ops.calls.get("lookup_fwd", 0) > 0, "the interpreter did not run"
+    gout = torch.from_numpy(np.concatenate([g[sl] for g in grads], 1)).to(out.dtype)
+    out.backward(gout)
+    dp_grads = [p.grad for layer in de.dp_layers for p in layer.parameters()]
+    return out.detach().float().numpy(), dp_grads
+
+  results = dry_run.run_ranks(sim, rank_fn)
+  ref_tables = [t.copy() for t in tables]
+  # replicated tables are not updated by the engine (their dense gradient goes to the all-reduce)
+  ref_outs = reference_step(ref_tables, imap, glob, combiners, grads, 0.5, world, kind, {})
+  ref_grads = None
+  if kind == "none":
+    ref_outs, ref_grads = ref_outs
+  tol = 1e-4 if dtype == torch.float32 else 3e-2
+  for r, (out, dp_grads) in enumerate(results):
+    exp = np.concatenate([o[r * lb:(r + 1) * lb] for o in ref_outs], 1)
+    np.testing.assert_allclose(out, exp, rtol=tol, atol=tol, err_msg=f"forward, rank {r}")
+  if ref_grads is not None:
+    # no fused optimizer: the engine returns deduplicated sparse gradients (reference semantics)
+    got_g = assemble(des, _dense_grad)
+    for t in range(n_tables):
+      if t not in dp_tables:
+        np.testing.assert_allclose(got_g[t], ref_grads[t], rtol=10 * tol, atol=10 * tol,
+                                   err_msg=f"sparse gradient of table {t}")
+  got = assemble(des)
+  for t in range(n_tables):
+    if t in dp_tables:
+      np.testing.assert_allclose(got[t], tables[t], rtol=0, atol=0)  # untouched by the engine
+      continue
+    np.testing.assert_allclose(got[t], ref_tables[t], rtol=10 * tol, atol=10 * tol,
+                               err_msg=f"table {t} after the {kind} step")
+  # dense gradients of replicated tables: local-batch contribution of each rank
+  for j, t in enumerate(st.table_groups[0]):
+    for r, (_, dp_grads) in enumerate(results):
+      exp = np.zeros_like(tables[t])
+      for i, ti in enumerate(imap):
+        if ti == t:
+          assert not rag[i]
+          ids = glob[i][r * lb:(r + 1) * lb]
+          n = ids.shape[1]
+          g = grads[i][r * lb:(r + 1) * lb] / (n if combiners[t] == "mean" else 1)
+          np.add.at(exp, ids.reshape(-1), np.repeat(g, n, axis=0))
+      np.testing.assert_allclose(dp_grads[j].numpy(), exp, rtol=10 * tol, atol=10 * tol)
+  return "ok"
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_random_plans_sgd(world):
+  outcomes = [run_plan(1000 * world + s, world, "sgd") for s in range(12)]
+  assert outcomes.count("ok") >= 8, outcomes
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("kind", ["adagrad", "rowwise_adagrad", "adam"])
+def test_random_plans_stateful_optimizers(world, kind):
+  outcomes = [run_plan(5000 * world + s, world, kind) for s in range(8)]
+  assert outcomes.count("ok") >= 5, outcomes
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_random_plans_sparse_gradients(world):
+  outcomes = [run_plan(3000 * world + s, world, "none") for s in range(8)]
+  assert outcomes.count("ok") >= 5, outcomes
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("kind", ["sgd", "adagrad"])
+def test_random_plans_ragged(world, kind):
+  outcomes = [run_plan(7000 * world + s, world, kind, ragged=True) for s in range(8)]
+  assert outcomes.count("ok") >= 5, outcomes
+
+
+def test_bf16_activations_world4():
+  outcomes = [run_plan(9000 + s, 4, "sgd", torch.bfloat16) for s in range(6)]
+  assert outcomes.count("ok") >= 4, outcomes
+
+
+def test_out_of_bounds_descriptor_is_caught():
+  """A corrupted descriptor must trip the interpreter's address check, not pass silently."""
+  embs = [{"input_dim": 10, "output_dim": 8, "combiner": "sum"} for _ in range(2)]
+  sim, des = dry_run.build_engines(embs, 1)
+  de = des[0]
+  de.set_optimizer("sgd", lr=0.1)
+  ids = [torch.randint(0, 10, (4, 2)) for _ in range(2)]
+  de(ids, concat=True)
+  eng = de._engine
+  eng.cdesc_np[0]["row_base"] = 1000  # beyond the fused table
+  eng._upload()
+  with pytest.raises((RuntimeError, IndexError)):
+    eng._run_forward()
