@@ -635,7 +635,12 @@ class FusedEngine:
       w = _weight(layer)
       lo, hi = bounds[m], bounds[m + 1]
       ids = (emit_keys[lo:hi] - bases[m]).unsqueeze(0).to(w.device)
-      rows = emit_rows[lo:hi, :w.shape[1]].contiguous().to(w.device)
+      # a fresh [nnz, width] buffer with canonical strides: for nnz == 1 ``.contiguous()`` is a
+      # no-op on the padded view (row stride max_width) and PyTorch's sparse -> dense kernels
+      # then address the destination with that stride (heap overflow found by the plan fuzzer)
+      rows = torch.empty(hi - lo, w.shape[1], dtype=torch.float32, device=emit_rows.device)
+      rows.copy_(emit_rows[lo:hi, :w.shape[1]])
+      rows = rows.to(w.device)
       out.append(torch.sparse_coo_tensor(ids, rows, size=tuple(w.shape), is_coalesced=True,
                                          check_invariants=False))
     return out

@@ -252,3 +252,25 @@ def test_out_of_bounds_descriptor_is_caught():
   eng._upload()
   with pytest.raises((RuntimeError, IndexError)):
     eng._run_forward()
+
+
+def test_sparse_gradient_values_have_canonical_strides():
+  """One unique row of a table narrower than the widest one: the emitted values must not be a
+  padded view (PyTorch's sparse -> dense kernels address the destination with the values' row
+  stride; found by the fuzzer as an intermittent heap corruption at world size 8)."""
+  embs = [{"input_dim": 6, "output_dim": 4, "combiner": "sum"},
+          {"input_dim": 9, "output_dim": 8, "combiner": "sum"}]
+  _, des = dry_run.build_engines(embs, 1)
+  de = des[0]
+  ids = [torch.full((5, 2), 3, dtype=torch.int64), torch.randint(0, 9, (5, 2))]
+  out = de(ids, concat=True)
+  out.backward(torch.ones_like(out))
+  for p in de.parameters():
+    g = p.grad
+    assert g.is_sparse
+    v = g._values()
+    assert v.stride() == (v.shape[1], 1), (tuple(v.shape), v.stride())
+    dense = g.to_dense()
+    assert torch.isfinite(dense).all()
+  narrow = [p for p in de.parameters() if p.shape[1] == 4][0].grad.to_dense()
+  assert narrow[3].tolist() == [10.0] * 4 and float(narrow.abs().sum()) == 40.0
