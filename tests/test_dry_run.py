@@ -274,3 +274,90 @@ def test_sparse_gradient_values_have_canonical_strides():
     assert torch.isfinite(dense).all()
   narrow = [p for p in de.parameters() if p.shape[1] == 4][0].grad.to_dense()
   assert narrow[3].tolist() == [10.0] * 4 and float(narrow.abs().sum()) == 40.0
+
+
+def _run_steps(seed, world, kind, n_steps=3):
+  """Several steps on one plan, with a different local batch size on the second step (the
+  engines rebuild their buffers): optimizer state, row-slice partial buffers and id staging must
+  carry over / be reset correctly from step to step."""
+  rng = random.Random(seed)
+  nrng = np.random.default_rng(seed)
+  n_tables = rng.randint(world, 2 * world + 1)
+  sizes = [(rng.randint(5, 40), rng.choice([4, 8, 16])) for _ in range(n_tables)]
+  combiners = [rng.choice(["sum", "mean"]) for _ in sizes]
+  imap = list(range(n_tables)) + [rng.randint(0, n_tables - 1) for _ in range(2)]
+  hots = [rng.choice([1, 2, 3]) for _ in imap]
+  kw = {"strategy": rng.choice(["basic", "memory_balanced", "memory_optimized"]),
+        "input_table_map": imap}
+  if rng.random() < 0.5:
+    kw["column_slice_threshold"] = rng.choice([60, 150])
+  if world > 1 and rng.random() < 0.5:
+    kw["row_slice_threshold"] = 400
+  embs = [{"input_dim": r, "output_dim": w, "combiner": c} for (r, w), c in zip(sizes, combiners)]
+  try:
+    sim, des = dry_run.build_engines(embs, world, **kw)
+  except ValueError as e:
+    if "Not enough table" in str(e):
+      return "infeasible"
+    raise
+  tables = [nrng.standard_normal(s).astype(np.float32) for s in sizes]
+  lr = 0.3
+  for de in des:
+    de.set_weights(tables)
+    de.set_optimizer(kind, lr=lr)
+  ref = [t.copy() for t in tables]
+  state = {}
+  for step in range(n_steps):
+    lb = [3, 5, 3, 2][step % 4]
+    B = lb * world
+    glob = [nrng.integers(0, sizes[t][0], size=(B, h)) for t, h in zip(imap, hots)]
+    grads = [nrng.standard_normal((B, sizes[t][1])).astype(np.float32) * 0.1 for t in imap]
+
+    def rank_fn(r, lb=lb, glob=glob, grads=grads):
+      inputs = [torch.from_numpy(g[r * lb:(r + 1) * lb]) for g in glob]
+      out = des[r](inputs, concat=True)
+      out.backward(torch.from_numpy(np.concatenate([g[r * lb:(r + 1) * lb] for g in grads], 1)))
+      return out.detach().numpy()
+
+    outs = dry_run.run_ranks(sim, rank_fn)
+    # reference: forward on the current tables, then the update
+    dense = [np.zeros_like(t) for t in ref]
+    exp_cols = []
+    for i, t in enumerate(imap):
+      n = glob[i].shape[1]
+      scale = 1.0 / n if combiners[t] == "mean" else 1.0
+      exp_cols.append(ref[t][glob[i]].sum(1) * scale)
+      np.add.at(dense[t], glob[i].reshape(-1), np.repeat(grads[i] * scale, n, axis=0))
+    exp = np.concatenate(exp_cols, 1)
+    for r in range(world):
+      np.testing.assert_allclose(outs[r], exp[r * lb:(r + 1) * lb], rtol=2e-4, atol=2e-4,
+                                 err_msg=f"step {step} forward rank {r}")
+    t_step = step + 1
+    for t, g in enumerate(dense):
+      g = g / world
+      touched = np.abs(g).sum(1) != 0
+      if kind == "sgd":
+        ref[t] -= lr * g
+      elif kind == "adagrad":
+        acc = state.setdefault(t, np.full_like(ref[t], 0.1))
+        acc[touched] += g[touched]**2
+        ref[t][touched] -= lr * g[touched] / (np.sqrt(acc[touched]) + 1e-7)
+      elif kind == "adam":
+        m, v = state.setdefault(t, (np.zeros_like(ref[t]), np.zeros_like(ref[t])))
+        m[touched] = 0.9 * m[touched] + 0.1 * g[touched]
+        v[touched] = 0.999 * v[touched] + 0.001 * g[touched]**2
+        mh = m[touched] / (1 - 0.9**t_step)
+        vh = v[touched] / (1 - 0.999**t_step)
+        ref[t][touched] -= lr * mh / (np.sqrt(vh) + 1e-8)
+  got = assemble(des)
+  for t in range(n_tables):
+    np.testing.assert_allclose(got[t], ref[t], rtol=2e-3, atol=2e-3,
+                               err_msg=f"table {t} after {n_steps} {kind} steps")
+  return "ok"
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("kind", ["sgd", "adagrad", "adam"])
+def test_multi_step_with_batch_size_change(world, kind):
+  outcomes = [_run_steps(400 * world + s, world, kind) for s in range(3)]
+  assert outcomes.count("ok") >= 2, outcomes
