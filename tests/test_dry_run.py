@@ -210,15 +210,15 @@ def run_plan(seed, world, kind="sgd", dtype=torch.float32, ragged=False):
 
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 def test_random_plans_sgd(world):
-  outcomes = [run_plan(1000 * world + s, world, "sgd") for s in range(12)]
-  assert outcomes.count("ok") >= 8, outcomes
+  outcomes = [run_plan(1000 * world + s, world, "sgd") for s in range(8)]
+  assert outcomes.count("ok") >= 5, outcomes
 
 
 @pytest.mark.parametrize("world", [1, 2, 4])
 @pytest.mark.parametrize("kind", ["adagrad", "rowwise_adagrad", "adam"])
 def test_random_plans_stateful_optimizers(world, kind):
-  outcomes = [run_plan(5000 * world + s, world, kind) for s in range(8)]
-  assert outcomes.count("ok") >= 5, outcomes
+  outcomes = [run_plan(5000 * world + s, world, kind) for s in range(5)]
+  assert outcomes.count("ok") >= 3, outcomes
 
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
@@ -230,8 +230,8 @@ def test_random_plans_sparse_gradients(world):
 @pytest.mark.parametrize("world", [1, 2, 4])
 @pytest.mark.parametrize("kind", ["sgd", "adagrad"])
 def test_random_plans_ragged(world, kind):
-  outcomes = [run_plan(7000 * world + s, world, kind, ragged=True) for s in range(8)]
-  assert outcomes.count("ok") >= 5, outcomes
+  outcomes = [run_plan(7000 * world + s, world, kind, ragged=True) for s in range(5)]
+  assert outcomes.count("ok") >= 3, outcomes
 
 
 def test_bf16_activations_world4():
