@@ -364,3 +364,28 @@ def test_multi_step_with_batch_size_change(world, kind):
   outcomes = [_run_steps(400 * world + s, world, kind, n_steps=3 if world < 8 else 2)
               for s in range(n)]
   assert outcomes.count("ok") >= n - 1, outcomes
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_tiny_table_split_path(world, monkeypatch):
+  """DE_B200_TINY_TABLES=1: one-hot inputs of tables with <= 64 rows go through the
+  shared-memory pre-reduction launch, everything else through the RED scatter; together they
+  must still produce the plain SGD update."""
+  monkeypatch.setenv("DE_B200_TINY_TABLES", "1")
+  seen = {"tiny": 0, "main": 0}
+  orig_tiny = dry_run.DryOps.tiny_scatter_add_bwd
+  orig_main = dry_run.DryOps.scatter_add_bwd
+
+  def tiny(self, *a, **k):
+    seen["tiny"] += 1
+    return orig_tiny(self, *a, **k)
+
+  def main(self, *a, **k):
+    seen["main"] += 1
+    return orig_main(self, *a, **k)
+
+  monkeypatch.setattr(dry_run.DryOps, "tiny_scatter_add_bwd", tiny)
+  monkeypatch.setattr(dry_run.DryOps, "scatter_add_bwd", main)
+  outcomes = [run_plan(8800 * world + s, world, "sgd") for s in range(8)]
+  assert outcomes.count("ok") >= 5, outcomes
+  assert seen["tiny"] > 0 and seen["main"] > seen["tiny"]  # tiny calls main once internally
