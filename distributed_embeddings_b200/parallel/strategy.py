@@ -408,3 +408,60 @@ class DistEmbeddingStrategy:
       dp = sum(_numel(c) for c in self.dp_configs)
       rep.append({"rank": r, "hbm_elements": hbm + row + dp, "host_elements": host})
     return rep
+
+  def traffic_report(self, global_batch: int, hotness: Optional[Sequence[int]] = None,
+                     activation_bytes: int = 2, id_bytes: int = 4) -> Dict[str, Any]:
+    """Per-rank bytes per step implied by the plan (forward; the backward moves the same
+    activation bytes in the other direction): rows gathered from the tables, pooled vectors
+    leaving the rank over NVLink, ids pulled from the other ranks.  ``hotness[i]`` is the number
+    of ids per sample of input ``i`` (default 1).  The step time of the embedding exchange is set
+    by the most loaded rank, so ``imbalance`` (max / mean) is what a threshold search minimises.
+    """
+    w_ = self.world_size
+    n_inputs = len(self.input_table_map)
+    hot = [1] * n_inputs if hotness is None else [int(h) for h in hotness]
+    if len(hot) != n_inputs:
+      raise ValueError(f"expected {n_inputs} hotness values, got {len(hot)}")
+    away = (w_ - 1) / w_ if w_ > 1 else 0.0
+    local_batch = global_batch // w_
+    ranks = [{"rank": r, "gather_bytes": 0.0, "nvlink_out_bytes": 0.0, "id_pull_bytes": 0.0,
+              "lookups": 0.0} for r in range(w_)]
+    # table-parallel / column-sliced: the owner looks up the global batch of its inputs
+    for r in range(w_):
+      for li, gi_group in enumerate(self.input_ids_list[r] if self.table_groups[1] else []):
+        gi = self.input_groups[1][gi_group]
+        width = int(self.local_configs[r][self.local_maps[r][li]]["output_dim"])
+        n_ids = global_batch * hot[gi]
+        ranks[r]["lookups"] += n_ids
+        ranks[r]["gather_bytes"] += n_ids * width * 4
+        ranks[r]["nvlink_out_bytes"] += global_batch * width * activation_bytes * away
+        ranks[r]["id_pull_bytes"] += n_ids * id_bytes * away
+    # row-sliced: every rank sees all ids, gathers its share, sends fp32 partial pools
+    for j, gi in enumerate(self.input_groups[2]):
+      t = self.table_groups[2][self.map_groups[2][j]]
+      width = int(self.global_configs[t]["output_dim"])
+      n_ids = global_batch * hot[gi]
+      for r in range(w_):
+        ranks[r]["lookups"] += n_ids / w_
+        ranks[r]["gather_bytes"] += n_ids / w_ * width * 4
+        ranks[r]["nvlink_out_bytes"] += global_batch * width * 4 * away
+        ranks[r]["id_pull_bytes"] += n_ids * id_bytes * away
+    # replicated: local batch only, nothing on the wire
+    for j, gi in enumerate(self.input_groups[0]):
+      t = self.table_groups[0][self.map_groups[0][j]]
+      width = int(self.global_configs[t]["output_dim"])
+      for r in range(w_):
+        ranks[r]["lookups"] += local_batch * hot[gi]
+        ranks[r]["gather_bytes"] += local_batch * hot[gi] * width * 4
+
+    def imbalance(key):
+      vals = [x[key] for x in ranks]
+      mean = sum(vals) / len(vals)
+      return max(vals) / mean if mean > 0 else 1.0
+
+    return {"ranks": ranks,
+            "max_gather_bytes": max(x["gather_bytes"] for x in ranks),
+            "max_nvlink_out_bytes": max(x["nvlink_out_bytes"] for x in ranks),
+            "gather_imbalance": imbalance("gather_bytes"),
+            "nvlink_imbalance": imbalance("nvlink_out_bytes")}
+

@@ -169,3 +169,33 @@ def test_fingerprint_is_stable():
   b = DistEmbeddingStrategy(cfgs(26 * [[1000, 128]]), 8, "memory_balanced").fingerprint()
   c = DistEmbeddingStrategy(cfgs(26 * [[1000, 128]]), 8, "basic").fingerprint()
   assert a == b and a != c
+
+
+def test_traffic_report_dlrm_mlperf():
+  """Bytes per step implied by a plan: the 1-GPU gather volume of the MLPerf DLRM is the
+  872 MB measured with ncu (profiles/README.md), and column slicing the six big tables evens
+  out the 8-GPU load."""
+  from distributed_embeddings_b200.models.dlrm import mlperf_table_sizes
+  cfgs = [{"input_dim": s, "output_dim": 128, "combiner": None} for s in mlperf_table_sizes()]
+  one = DistEmbeddingStrategy(cfgs, 1, "memory_balanced").traffic_report(65536)
+  assert one["max_gather_bytes"] == 65536 * 26 * 128 * 4 and one["max_nvlink_out_bytes"] == 0
+  plain = DistEmbeddingStrategy(cfgs, 8, "memory_balanced").traffic_report(65536)
+  sliced = DistEmbeddingStrategy(cfgs, 8, "memory_balanced",
+                                 column_slice_threshold=2**32).traffic_report(65536)
+  assert sliced["nvlink_imbalance"] < plain["nvlink_imbalance"] <= 1.3
+  total_out = sum(r["nvlink_out_bytes"] for r in sliced["ranks"])
+  assert total_out == pytest.approx(65536 * 26 * 128 * 2 * 7 / 8)
+  # multi-hot, row slices and replicated tables are accounted separately
+  cfgs = [{"input_dim": 1000, "output_dim": 16, "combiner": "sum"},
+          {"input_dim": 10, "output_dim": 8, "combiner": "sum"},
+          {"input_dim": 100000, "output_dim": 32, "combiner": "sum"}]
+  st = DistEmbeddingStrategy(cfgs, 4, "basic", data_parallel_threshold=100,
+                             row_slice_threshold=1000000)
+  rep = st.traffic_report(4096, hotness=[3, 1, 5])
+  assert st.table_groups == [[1], [0], [2]]
+  r0 = rep["ranks"][0]
+  # the single table-parallel table is column sliced onto all 4 ranks (fewer tables than
+  # workers): each looks up the whole batch; replicated: 1024 local lookups per rank; row slice:
+  # a quarter of the 4096 x 5 ids on every rank
+  assert sum(r["lookups"] for r in rep["ranks"]) == 4 * 4096 * 3 + 4 * 1024 + 4096 * 5
+  assert r0["nvlink_out_bytes"] >= 4096 * 32 * 4 * 3 / 4
