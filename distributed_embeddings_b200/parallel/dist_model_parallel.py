@@ -27,7 +27,7 @@ from ..layers.embedding import Embedding, config_from_layer
 from ..ops.ragged import RaggedIds, SparseIds
 from ..utils import initializers
 from .comm import dist_ready
-from .strategy import DistEmbeddingStrategy, STRATEGIES
+from .strategy import DistEmbeddingStrategy, STRATEGIES, suggest_column_slice_threshold
 
 
 # ------------------------------------------------------------------------- autograd collectives
@@ -209,7 +209,8 @@ class DistributedEmbedding(nn.Module):
       ``get_config()`` (with ``input_dim``/``output_dim``) and ``from_config()``.
     strategy: ``basic`` | ``memory_balanced`` | ``memory_optimized``.
     column_slice_threshold: tables with more elements are column sliced (power-of-two count);
-      None slices only when there are fewer tables than workers.
+      None slices only when there are fewer tables than workers; ``"auto"`` picks the threshold
+      that balances the per-rank gather / NVLink bytes (``suggest_column_slice_threshold``).
     row_slice_threshold: tables with at least this many elements are row sliced over all workers.
     dp_input: True -> every rank passes its local batch of *all* features; False -> every rank
       passes the *global* batch of its own features (``strategy.input_ids_list[rank]``).
@@ -267,6 +268,14 @@ class DistributedEmbedding(nn.Module):
     self.mp_grad_scale = 1.0 / self.world_size
 
     configs = [config_from_layer(e) for e in embeddings]
+    if column_slice_threshold == "auto":
+      # balance the NVLink / gather bytes of the most loaded rank (see traffic_report)
+      column_slice_threshold = suggest_column_slice_threshold(
+          configs, self.world_size, strategy, input_table_map=input_table_map,
+          row_slice_threshold=self.row_slice_threshold,
+          data_parallel_threshold=self.data_parallel_threshold,
+          gpu_embedding_size=gpu_embedding_size)
+      self.column_slice_threshold = column_slice_threshold
     self.strategy = DistEmbeddingStrategy(configs,
                                           self.world_size,
                                           strategy,

@@ -465,3 +465,32 @@ class DistEmbeddingStrategy:
             "gather_imbalance": imbalance("gather_bytes"),
             "nvlink_imbalance": imbalance("nvlink_out_bytes")}
 
+
+def suggest_column_slice_threshold(embeddings: Sequence[Any], world_size: int,
+                                   strategy: str = "memory_balanced",
+                                   input_table_map: Optional[Sequence[int]] = None,
+                                   hotness: Optional[Sequence[int]] = None,
+                                   min_slice_width: int = 64, **plan_kwargs) -> Optional[int]:
+  """Column-slice threshold (``None`` or a power of two) that minimises the bytes the most
+  loaded rank gathers and sends per step (``traffic_report``), keeping every slice at least
+  ``min_slice_width`` columns wide (narrow slices waste the 128-byte vector accesses of the
+  lookup kernels).  What ``column_slice_threshold="auto"`` of ``DistributedEmbedding`` uses."""
+  best, best_cost = None, None
+  for thr in [None] + [2**k for k in range(34, 22, -1)]:
+    try:
+      st = DistEmbeddingStrategy(embeddings, world_size, strategy, input_table_map=input_table_map,
+                                 column_slice_threshold=thr, **plan_kwargs)
+    except ValueError:
+      continue
+    if st.table_groups[1] and any(not st.local_configs[r] for r in range(world_size)):
+      continue
+    widths = [int(c["output_dim"]) for r in range(world_size) for c in st.local_configs[r]]
+    full = [int(c["output_dim"]) for c in st.global_configs]
+    if widths and min(widths) < min(min_slice_width, min(full)):
+      continue
+    rep = st.traffic_report(world_size * 1024, hotness)
+    cost = (rep["max_nvlink_out_bytes"], rep["max_gather_bytes"])
+    if best_cost is None or cost < best_cost:
+      best, best_cost = thr, cost
+  return best
+

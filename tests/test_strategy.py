@@ -199,3 +199,22 @@ def test_traffic_report_dlrm_mlperf():
   # a quarter of the 4096 x 5 ids on every rank
   assert sum(r["lookups"] for r in rep["ranks"]) == 4 * 4096 * 3 + 4 * 1024 + 4096 * 5
   assert r0["nvlink_out_bytes"] >= 4096 * 32 * 4 * 3 / 4
+
+
+def test_auto_column_slice_threshold():
+  from distributed_embeddings_b200 import DistributedEmbedding
+  from distributed_embeddings_b200.models.dlrm import mlperf_table_sizes
+  from distributed_embeddings_b200.parallel.strategy import suggest_column_slice_threshold
+  cfgs = [{"input_dim": s, "output_dim": 128, "combiner": None} for s in mlperf_table_sizes()]
+  assert [suggest_column_slice_threshold(cfgs, w) for w in (1, 2, 4, 8)] == \
+      [None, None, None, 2**32]
+  # the wrapper accepts "auto" (planning only: no process group needed with explicit rank/world)
+  small = [{"input_dim": 5000, "output_dim": 128, "combiner": "sum"}] + \
+      [{"input_dim": 50, "output_dim": 128, "combiner": "sum"} for _ in range(3)]
+  de = DistributedEmbedding(small, strategy="memory_balanced", column_slice_threshold="auto",
+                            device="cpu", backend="torch", world_size=4, rank=0)
+  rep = de.strategy.traffic_report(4096)
+  base = DistributedEmbedding(small, strategy="memory_balanced", device="cpu", backend="torch",
+                              world_size=4, rank=0).strategy.traffic_report(4096)
+  assert rep["max_nvlink_out_bytes"] <= base["max_nvlink_out_bytes"]
+  assert min(c["output_dim"] for r in range(4) for c in de.strategy.local_configs[r]) >= 64
