@@ -135,7 +135,7 @@ class SyntheticModel(_SyntheticBase):
                device=None, compute_dtype=torch.float32, backend="auto",
                row_slice_threshold=None, data_parallel_threshold=None, strategy="memory_balanced"):
     super().__init__()
-    tables, imap, _ = expand(model_config)
+    tables, imap, hots = expand(model_config)[:3]
     self.input_table_map = imap
     self.compute_dtype = compute_dtype
     self.interact_stride = model_config.interact_stride
@@ -147,7 +147,7 @@ class SyntheticModel(_SyntheticBase):
                                           row_slice_threshold=row_slice_threshold,
                                           data_parallel_threshold=data_parallel_threshold,
                                           device=device, compute_dtype=compute_dtype,
-                                          backend=backend)
+                                          backend=backend, input_hotness=list(hots))
     total = sum(tables[t][1] for t in imap)
     if self.interact_stride is not None:
       total = -(-total // self.interact_stride)
@@ -166,7 +166,7 @@ class SyntheticModelNative(_SyntheticBase):
 
   def __init__(self, model_config: ModelConfig, device=None, compute_dtype=torch.float32):
     super().__init__()
-    tables, imap, _ = expand(model_config)
+    tables, imap, hots = expand(model_config)[:3]
     self.input_table_map = imap
     self.compute_dtype = compute_dtype
     self.interact_stride = model_config.interact_stride

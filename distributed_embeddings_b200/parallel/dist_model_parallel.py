@@ -207,7 +207,8 @@ class DistributedEmbedding(nn.Module):
     embeddings: list of (unplaced) embedding layers: ``distributed_embeddings_b200.Embedding``,
       ``torch.nn.Embedding`` / ``EmbeddingBag``, config dicts, or user layers exposing
       ``get_config()`` (with ``input_dim``/``output_dim``) and ``from_config()``.
-    strategy: ``basic`` | ``memory_balanced`` | ``memory_optimized``.
+    strategy: ``basic`` | ``memory_balanced`` | ``memory_optimized`` | ``traffic_balanced``
+      (balances the per-step work of the ranks using ``input_hotness``; not in the reference).
     column_slice_threshold: tables with more elements are column sliced (power-of-two count);
       None slices only when there are fewer tables than workers; ``"auto"`` picks the threshold
       that balances the per-rank gather / NVLink bytes (``suggest_column_slice_threshold``).
@@ -218,6 +219,7 @@ class DistributedEmbedding(nn.Module):
     data_parallel_threshold: tables with at most this many elements are replicated.
     gpu_embedding_size: per-rank HBM element budget; the largest table-parallel tables beyond it
       live in pinned host memory.
+    input_hotness: ids per sample of every input, for ``traffic_balanced`` (keyword only).
     device / process_group / backend / compute_dtype: execution placement (keyword only).
       ``compute_dtype`` is the dtype of the returned activations (bf16 halves the bytes on the
       wire like the reference's mixed precision mode, dist_model_parallel.py:866).
@@ -238,7 +240,8 @@ class DistributedEmbedding(nn.Module):
                backend: str = "auto",
                compute_dtype: Optional[torch.dtype] = None,
                rank: Optional[int] = None,
-               world_size: Optional[int] = None):
+               world_size: Optional[int] = None,
+               input_hotness: Optional[Sequence[int]] = None):
     super().__init__()
     if strategy not in STRATEGIES:
       raise ValueError(f"Unsupported shard strategy {strategy}")
@@ -274,7 +277,8 @@ class DistributedEmbedding(nn.Module):
           configs, self.world_size, strategy, input_table_map=input_table_map,
           row_slice_threshold=self.row_slice_threshold,
           data_parallel_threshold=self.data_parallel_threshold,
-          gpu_embedding_size=gpu_embedding_size)
+          gpu_embedding_size=gpu_embedding_size, hotness=input_hotness,
+          input_hotness=input_hotness)
       self.column_slice_threshold = column_slice_threshold
     self.strategy = DistEmbeddingStrategy(configs,
                                           self.world_size,
@@ -283,7 +287,8 @@ class DistributedEmbedding(nn.Module):
                                           column_slice_threshold=column_slice_threshold,
                                           row_slice_threshold=self.row_slice_threshold,
                                           data_parallel_threshold=self.data_parallel_threshold,
-                                          gpu_embedding_size=gpu_embedding_size)
+                                          gpu_embedding_size=gpu_embedding_size,
+                                          input_hotness=input_hotness)
     st = self.strategy
     self.num_inputs = len(st.input_table_map)
 

@@ -19,7 +19,7 @@ import json
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Sequence
 
-STRATEGIES = ("basic", "memory_balanced", "memory_optimized")
+STRATEGIES = ("basic", "memory_balanced", "memory_optimized", "traffic_balanced")
 
 
 def _numel(cfg: Dict[str, Any]) -> int:
@@ -65,7 +65,10 @@ class DistEmbeddingStrategy:
       ``input_dim`` and ``output_dim``), or plain config dicts.
     world_size: number of model-parallel workers.
     strategy: ``basic`` (round robin) | ``memory_balanced`` (size-sorted snake, even table
-      count) | ``memory_optimized`` (greedy least-loaded).
+      count) | ``memory_optimized`` (greedy least-loaded memory) | ``traffic_balanced`` (greedy
+      least-loaded *work*: ids looked up x slice width, i.e. the bytes a rank gathers and sends
+      per step; not in the reference - with multi-hot features the size-based placements leave
+      the busiest rank of the synthetic models with 2-2.5x the mean work).
     input_table_map: ``input[i]`` reads ``table[input_table_map[i]]``; None = identity.
     column_slice_threshold: tables with more elements are split along width into the smallest
       power-of-two number of slices that brings each slice under the threshold.
@@ -74,6 +77,7 @@ class DistEmbeddingStrategy:
     data_parallel_threshold: tables with at most this many elements are replicated.
     gpu_embedding_size: per-rank element budget for table-parallel tables kept in HBM; the
       largest tables beyond it are placed in host memory.
+    input_hotness: ids per sample of every input (default 1); only ``traffic_balanced`` uses it.
 
   Attributes mirror the reference (DMP:319-345) so that user code such as
   ``strategy.input_ids_list[rank]`` keeps working.
@@ -87,7 +91,8 @@ class DistEmbeddingStrategy:
                column_slice_threshold: Optional[int] = None,
                row_slice_threshold: Optional[int] = None,
                data_parallel_threshold: Optional[int] = None,
-               gpu_embedding_size: Optional[int] = None):
+               gpu_embedding_size: Optional[int] = None,
+               input_hotness: Optional[Sequence[int]] = None):
     if strategy not in STRATEGIES:
       raise ValueError(f"Unsupported shard strategy {strategy}")
     self.world_size = int(world_size)
@@ -106,6 +111,11 @@ class DistEmbeddingStrategy:
     if input_table_map is None:
       input_table_map = list(range(len(self.global_configs)))
     self.input_table_map = [int(t) for t in input_table_map]
+    if input_hotness is None:
+      input_hotness = [1] * len(self.input_table_map)
+    if len(input_hotness) != len(self.input_table_map):
+      raise ValueError("input_hotness needs one entry per input")
+    self.input_hotness = [max(1, int(h)) for h in input_hotness]
 
     self.table_groups = self._group_tables()
     self.input_groups, self.map_groups, self.rev_group_ids = self._group_inputs()
@@ -218,9 +228,20 @@ class DistEmbeddingStrategy:
       sizes += [largest // 2, largest // 2]
     return threshold
 
-  def _place(self, slice_table_ids: List[int], slice_sizes: List[int]) -> List[List[int]]:
+  def _place(self, slice_table_ids: List[int], slice_sizes: List[int],
+             slice_costs: Optional[List[int]] = None) -> List[List[int]]:
     """Distribute slices (identified by their table id) to ranks."""
     w = self.world_size
+    if self.strategy == "traffic_balanced":
+      # longest-processing-time greedy on the per-step work, memory as the tie breaker
+      todo = sorted(zip(slice_costs, slice_sizes, slice_table_ids), reverse=True)
+      bins = [[0, 0, r, []] for r in range(w)]  # work, memory, rank, tables
+      for cost, size, t in todo:
+        b = min(bins, key=lambda x: (x[0], x[1], x[2]))
+        b[0] += cost
+        b[1] += size
+        b[3].append(t)
+      return [b[3] for b in bins]
     if self.strategy == "basic":
       return [slice_table_ids[r::w] for r in range(w)]
     if self.strategy == "memory_balanced":
@@ -246,12 +267,31 @@ class DistEmbeddingStrategy:
       threshold = self._auto_threshold(configs)
 
     widths = [self.slice_widths(c, threshold, self.world_size) for c in configs]
-    flat_ids, flat_sizes = [], []
+    # per-sample work of every table of the group, in "rows of one column": every id is a row
+    # gathered (and read-modify-written in the backward), every input one pooled vector out and
+    # one gradient vector in over NVLink, worth about two row accesses each at the measured
+    # HBM / NVLink rates (profiles/README.md)
+    lookups = [0] * len(configs)
+    for k, t in enumerate(col_map):
+      lookups[t] += self.input_hotness[self.input_groups[1][k]] + 2
+    if self.strategy == "traffic_balanced" and self.world_size > 1:
+      # a table whose work alone exceeds a rank's fair share is column sliced further (power of
+      # two, slices stay >= 32 columns = one 128-byte row segment)
+      fair = sum(lookups[t] * int(c["output_dim"]) for t, c in enumerate(configs)) / self.world_size
+      for t, c in enumerate(configs):
+        width, n = int(c["output_dim"]), len(widths[t])
+        while lookups[t] * width / n > fair and 2 * n <= self.world_size and width // (2 * n) >= 32:
+          n *= 2
+        if n != len(widths[t]):
+          base, rem = divmod(width, n)
+          widths[t] = [base + (1 if i < rem else 0) for i in range(n)]
+    flat_ids, flat_sizes, flat_costs = [], [], []
     for t, ws in enumerate(widths):
       for w_ in ws:
         flat_ids.append(t)
         flat_sizes.append(int(configs[t]["input_dim"]) * w_)
-    placement = self._place(flat_ids, flat_sizes)
+        flat_costs.append(lookups[t] * w_)
+    placement = self._place(flat_ids, flat_sizes, flat_costs)
 
     # Hand out slices in rank order; slices of one table meeting on a rank are merged into one
     # wider shard.  Column ranges therefore grow with the rank, which is also the order in

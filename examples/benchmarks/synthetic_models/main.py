@@ -38,6 +38,10 @@ def main():
   p.add_argument("--row_slice_threshold", type=int, default=None)
   p.add_argument("--data_parallel_threshold", type=int, default=None)
   p.add_argument("--embedding_api", default="de", choices=["native", "de"])
+  p.add_argument("--dist_strategy", default="memory_balanced",
+                 choices=["basic", "memory_balanced", "memory_optimized", "traffic_balanced"],
+                 help="placement; traffic_balanced evens out the per-rank lookups of the "
+                 "multi-hot features (memory_balanced is what the reference benchmark uses)")
   p.add_argument("--amp", action="store_true", help="bf16 activations / MLP")
   p.add_argument("--backend", default="auto", choices=["auto", "fused", "torch"])
   p.add_argument("--row_scale", type=float, default=1.0, help="shrink tables (smoke runs)")
@@ -67,7 +71,8 @@ def main():
     model = SyntheticModel(cfg, column_slice_threshold=args.column_slice_threshold,
                            dp_input=args.dp_input, device=device, compute_dtype=dtype,
                            backend=args.backend, row_slice_threshold=args.row_slice_threshold,
-                           data_parallel_threshold=args.data_parallel_threshold)
+                           data_parallel_threshold=args.data_parallel_threshold,
+                           strategy=args.dist_strategy)
     mp_ids = None if args.dp_input else model.embedding.strategy.input_ids_list[rank]
   else:
     if not args.dp_input or args.column_slice_threshold is not None:

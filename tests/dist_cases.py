@@ -509,7 +509,7 @@ def case_fuzz(rank, world, device, backend, n_seeds=6, seed0=100, **kw):
   rejected = 0
   for seed in range(seed0, seed0 + n_seeds):
     rng = random.Random(seed * 7919)
-    strategy = rng.choice(["basic", "memory_balanced", "memory_optimized"])
+    strategy = rng.choice(["basic", "memory_balanced", "memory_optimized", "traffic_balanced"])
     num_tables = rng.randint(world, 3 * world)
     table_sizes = [[rng.randint(4, 40), rng.choice([4, 6, 8, 12, 16])] for _ in range(num_tables)]
     opts = {}

@@ -101,8 +101,11 @@ def run_plan(seed, world, kind="sgd", dtype=torch.float32, ragged=False):
   if sorted(set(imap)) != list(range(n_tables)):
     imap = list(range(n_tables))
   hots = {t: rng.choice([1, 1, 2, 3]) for t in range(n_tables)}
-  kw = {"strategy": rng.choice(["basic", "memory_balanced", "memory_optimized"]),
+  kw = {"strategy": rng.choice(["basic", "memory_balanced", "memory_optimized",
+                                 "traffic_balanced"]),
         "input_table_map": imap}
+  if kw["strategy"] == "traffic_balanced" and not ragged and kind != "rowwise_adagrad":
+    kw["input_hotness"] = [hots[t] for t in imap]
   # a column slice keeps its own per-row accumulator (mean of g^2 over *its* columns), so the
   # unsharded reference only applies to row-wise Adagrad when tables are not column sliced
   if rng.random() < 0.5 and kind != "rowwise_adagrad":
@@ -288,8 +291,9 @@ def _run_steps(seed, world, kind, n_steps=3):
   combiners = [rng.choice(["sum", "mean"]) for _ in sizes]
   imap = list(range(n_tables)) + [rng.randint(0, n_tables - 1) for _ in range(2)]
   hots = [rng.choice([1, 2, 3]) for _ in imap]
-  kw = {"strategy": rng.choice(["basic", "memory_balanced", "memory_optimized"]),
-        "input_table_map": imap}
+  kw = {"strategy": rng.choice(["basic", "memory_balanced", "memory_optimized",
+                                 "traffic_balanced"]),
+        "input_table_map": imap, "input_hotness": hots}
   if rng.random() < 0.5:
     kw["column_slice_threshold"] = rng.choice([60, 150])
   if world > 1 and rng.random() < 0.5:

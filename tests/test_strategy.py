@@ -218,3 +218,36 @@ def test_auto_column_slice_threshold():
                               world_size=4, rank=0).strategy.traffic_report(4096)
   assert rep["max_nvlink_out_bytes"] <= base["max_nvlink_out_bytes"]
   assert min(c["output_dim"] for r in range(4) for c in de.strategy.local_configs[r]) >= 64
+
+
+def test_traffic_balanced_placement():
+  """The work-balancing placement (not in the reference): on the synthetic "small" model at 8
+  ranks the size-based snake leaves one rank with 2.5x the mean gather bytes."""
+  from distributed_embeddings_b200.models.configs import expand, synthetic_models_v3
+  tables, imap, hots = expand(synthetic_models_v3["small"])[:3]
+  cfgs = [{"input_dim": int(r), "output_dim": int(w), "combiner": "sum"} for r, w in tables]
+  mem = DistEmbeddingStrategy(cfgs, 8, "memory_balanced", input_table_map=imap)
+  tra = DistEmbeddingStrategy(cfgs, 8, "traffic_balanced", input_table_map=imap,
+                              input_hotness=hots)
+  a, b = mem.traffic_report(65536, hots), tra.traffic_report(65536, hots)
+  assert a["gather_imbalance"] > 2.0 and b["gather_imbalance"] < 1.25
+  assert b["max_gather_bytes"] < 0.6 * a["max_gather_bytes"]
+  assert b["nvlink_imbalance"] < 1.5
+  # every table is still placed exactly once per column and the plan is deterministic
+  cover = {}
+  for r, shards in enumerate(tra.shards):
+    for s in shards:
+      cover.setdefault(s.table, []).append((s.col_start, s.col_end))
+  for t, pieces in cover.items():
+    pieces.sort()
+    assert pieces[0][0] == 0 and all(x[1] == y[0] for x, y in zip(pieces, pieces[1:]))
+  again = DistEmbeddingStrategy(cfgs, 8, "traffic_balanced", input_table_map=imap,
+                                input_hotness=hots)
+  assert again.fingerprint() == tra.fingerprint()
+  # a single dominant multi-hot table gets column sliced beyond what its size asks for
+  hot = [{"input_dim": 1000, "output_dim": 128, "combiner": "sum"}] + \
+      [{"input_dim": 1000, "output_dim": 128, "combiner": "sum"} for _ in range(7)]
+  st = DistEmbeddingStrategy(hot, 4, "traffic_balanced", input_hotness=[50] + [1] * 7)
+  assert len([s for sh in st.shards for s in sh if s.table == 0]) == 4
+  with pytest.raises(ValueError):
+    DistEmbeddingStrategy(hot, 4, "traffic_balanced", input_hotness=[1, 2])

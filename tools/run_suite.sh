@@ -15,6 +15,9 @@ run 29604 200 $SYN --model tiny --optimizer adagrad --batch_size 65536 --alpha 1
 run 29605 240 $SYN --model small --optimizer adagrad --batch_size 65536 --alpha 1.05 --num_steps 30 --num_data_batches 2 --amp
 run 29606 300 $SYN --model medium --optimizer adagrad --batch_size 65536 --alpha 1.05 --num_steps 20 --num_data_batches 1 --amp
 run 29607 200 tools/bench_integer_lookup_dlrm.py --steps 30
+# work-balancing placement (not in the reference) vs the memory_balanced lines above
+run 29609 200 $SYN --model tiny --optimizer adagrad --batch_size 65536 --alpha 1.05 --num_steps 30 --num_data_batches 2 --amp --dist_strategy traffic_balanced
+run 29610 240 $SYN --model small --optimizer adagrad --batch_size 65536 --alpha 1.05 --num_steps 30 --num_data_batches 2 --amp --dist_strategy traffic_balanced
 if [ "$N" = "8" ]; then
   run 29608 420 $SYN --model large --optimizer rowwise_adagrad --batch_size 65536 --alpha 1.05 --num_steps 10 --num_data_batches 1 --amp --column_slice_threshold 1342177280
 fi
