@@ -213,8 +213,9 @@ def run_plan(seed, world, kind="sgd", dtype=torch.float32, ragged=False):
 
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 def test_random_plans_sgd(world):
-  outcomes = [run_plan(1000 * world + s, world, "sgd") for s in range(8)]
-  assert outcomes.count("ok") >= 5, outcomes
+  n = 8 if world < 8 else 4
+  outcomes = [run_plan(1000 * world + s, world, "sgd") for s in range(n)]
+  assert outcomes.count("ok") >= n // 2 + 1, outcomes
 
 
 @pytest.mark.parametrize("world", [1, 2, 4])
@@ -226,7 +227,7 @@ def test_random_plans_stateful_optimizers(world, kind):
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_random_plans_sparse_gradients(world):
-  n = 8 if world < 8 else 4
+  n = 8 if world < 8 else 3
   outcomes = [run_plan(3000 * world + s, world, "none") for s in range(n)]
   assert outcomes.count("ok") >= n // 2 + 1, outcomes
 
@@ -364,10 +365,10 @@ def _run_steps(seed, world, kind, n_steps=3):
 @pytest.mark.parametrize("world", [2, 8])
 @pytest.mark.parametrize("kind", ["sgd", "adagrad", "adam"])
 def test_multi_step_with_batch_size_change(world, kind):
-  n = 3 if world < 8 else 2
+  n = 3 if world < 8 else 1
   outcomes = [_run_steps(400 * world + s, world, kind, n_steps=3 if world < 8 else 2)
               for s in range(n)]
-  assert outcomes.count("ok") >= n - 1, outcomes
+  assert outcomes.count("ok") >= max(1, n - 1), outcomes
 
 
 @pytest.mark.parametrize("world", [1, 2, 4])
