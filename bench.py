@@ -44,8 +44,10 @@ def parse_args():
   p.add_argument("--lr", type=float, default=24.0)
   p.add_argument("--data-batches", type=int, default=4)
   p.add_argument("--no-e2e", action="store_true")
-  p.add_argument("--column-slice-threshold", default=None,
-                 help="elements; 'auto' = balance the looked-up columns per rank (slices >= 64 wide)")
+  p.add_argument("--column-slice-threshold", default="auto",
+                 help="elements, 'none', or 'auto' (default) = balance the looked-up columns per "
+                 "rank with slices >= 64 wide: 2^32 at 8 GPUs, no slicing at 1-4 (measured "
+                 "0.657 vs 0.662 ms at 8 GPUs)")
   p.add_argument("--cuda-graph", type=int, default=1)
   p.add_argument("--gemm", default="cublas", choices=["cublas", "fused_dgrad", "tcgen05", "tcgen05_pair"],
                  help="MLP GEMM path of the fast trainer (see models/dlrm_fast.py)")
@@ -200,7 +202,9 @@ def main():
   cst = args.column_slice_threshold
   if cst == "auto":
     cst = auto_column_slice_threshold(sizes, 128, world)
-  elif cst is not None:
+  elif cst is None or str(cst).lower() == "none":
+    cst = None
+  else:
     cst = int(cst)
   model = DLRM(sizes, device=device, compute_dtype=compute_dtype, backend=args.backend,
                column_slice_threshold=cst)

@@ -9,7 +9,7 @@ run() { # port, timeout, cmd...
   timeout $to $TR --master-port $port "$@" 2>&1 | grep -E '^\{' | tail -1 >> $OUT || echo "{\"failed\": \"$*\"}" >> $OUT
 }
 run 29601 240 bench.py --gpus $N --steps 50 --warmup 10
-run 29602 240 bench.py --gpus $N --steps 50 --warmup 10 --column-slice-threshold auto --no-e2e
+run 29602 240 bench.py --gpus $N --steps 50 --warmup 10 --column-slice-threshold none --no-e2e
 SYN=examples/benchmarks/synthetic_models/main.py
 run 29604 200 $SYN --model tiny --optimizer adagrad --batch_size 65536 --alpha 1.05 --num_steps 30 --num_data_batches 2 --amp
 run 29605 240 $SYN --model small --optimizer adagrad --batch_size 65536 --alpha 1.05 --num_steps 30 --num_data_batches 2 --amp
