@@ -48,6 +48,9 @@ def parse_args():
                  help="elements, 'none', or 'auto' (default) = balance the looked-up columns per "
                  "rank with slices >= 64 wide: 2^32 at 8 GPUs, no slicing at 1-4 (measured "
                  "0.657 vs 0.662 ms at 8 GPUs)")
+  p.add_argument("--data-parallel-threshold", type=int, default=None,
+                 help="replicate tables with at most this many elements (experimental in the fast "
+                 "trainer: e.g. 300000 replicates the 11 tiny MLPerf tables)")
   p.add_argument("--cuda-graph", type=int, default=1)
   p.add_argument("--gemm", default="cublas", choices=["cublas", "fused_dgrad", "tcgen05", "tcgen05_pair"],
                  help="MLP GEMM path of the fast trainer (see models/dlrm_fast.py)")
@@ -207,7 +210,7 @@ def main():
   else:
     cst = int(cst)
   model = DLRM(sizes, device=device, compute_dtype=compute_dtype, backend=args.backend,
-               column_slice_threshold=cst)
+               column_slice_threshold=cst, data_parallel_threshold=args.data_parallel_threshold)
   from distributed_embeddings_b200 import broadcast_variables
   broadcast_variables(model)
   use_fast = args.trainer == "fast" and args.backend == "fused"

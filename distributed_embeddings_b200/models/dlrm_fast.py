@@ -91,7 +91,21 @@ class DLRMTrainStep:
     if self.head.out_f != 1:
       raise ValueError("the top MLP must end in a single logit")
     layers = self.bottom + self.top + [self.head]
+    # replicated (data-parallel) embedding tables live in the flat dense buffers too: their
+    # local-batch gradient is scattered into the gradient bucket, all-reduced with the MLP
+    # gradients and applied by the same fused SGD kernel.  They come first so that they belong to
+    # the bucket that is reduced last (DE_B200_AR_OVERLAP).  Experimental: written after the
+    # round-1 GPU budget was spent (engine side validated in the plan interpreter).
+    self._dp_slots = []
     pos = 0
+    if len(self.emb.dp_layers):
+      if embedding_optimizer != "sgd":
+        raise ValueError("replicated tables in the fast step are updated by the dense SGD "
+                         "kernel: use embedding_optimizer='sgd' or data_parallel_threshold=None")
+      for layer in self.emb.dp_layers:
+        w = layer.embeddings
+        self._dp_slots.append((pos, tuple(w.shape)))
+        pos += _pad8(w.numel())
     for L in layers:
       L.w_off = pos
       pos += L.w_numel
@@ -113,6 +127,16 @@ class DLRMTrainStep:
       self.g32 = torch.zeros(pos, dtype=torch.float32, device=dev)
     # move the module parameters into the flat master buffer (strided views keep the module usable)
     with torch.no_grad():
+      dp_targets = []
+      for layer, (off, shape) in zip(self.emb.dp_layers, self._dp_slots):
+        n = shape[0] * shape[1]
+        view = self.p32[off:off + n].view(shape)
+        view.copy_(layer.embeddings.data)
+        layer.embeddings.data = view
+        dp_targets.append(self.g32[off:off + n].view(shape))
+      if self._dp_slots:
+        self.engine.set_dp_grad_targets(dp_targets)
+        self.engine._tables_dirty = True
       for L in layers:
         wv = self.p32[L.w_off:L.w_off + L.w_numel].view(L.out_f, L.in_pad)
         wv[:, :L.in_f].copy_(L.lin.weight)
@@ -283,6 +307,9 @@ class DLRMTrainStep:
       if i > 0:
         self._dgrad_relu(L, x, self.bottom[i - 1].dy, self.bottom[i - 1].gb)
     # dense gradient all-reduce (one NVLink kernel, averaged) + fused SGD / re-cast / zero
+    if self._dp_slots and self._side is not None:
+      # the replicated tables' gradients are produced by the embedding backward on the side stream
+      torch.cuda.current_stream().wait_stream(self._side)
     if getattr(self, "_w_used", False):  # join only a stream that took part in this step
       torch.cuda.current_stream().wait_stream(self._wstream)
       self._w_used = False

@@ -561,14 +561,48 @@ class FusedEngine:
     grads += self._backward_mp(bf16)
     return grads
 
+  def set_dp_grad_targets(self, targets: Optional[Sequence[torch.Tensor]]):
+    """Persistent dense-gradient buffers of the replicated tables, one fp32 ``[rows, width]``
+    tensor per ``de.dp_layers`` entry (e.g. slices of a flat all-reduce bucket).  The caller
+    zeroes them every step; :meth:`backward_inplace` accumulates the local-batch gradient into
+    them, so a hand-scheduled step can all-reduce and apply them with its dense parameters."""
+    if targets is not None:
+      targets = list(targets)
+      if len(targets) != len(self.de.dp_layers):
+        raise ValueError(f"expected {len(self.de.dp_layers)} targets, got {len(targets)}")
+      for t, layer in zip(targets, self.de.dp_layers):
+        w = _weight(layer)
+        if t.dtype != torch.float32 or tuple(t.shape) != tuple(w.shape) or not t.is_contiguous():
+          raise ValueError("dp gradient targets must be contiguous fp32 tensors of the table shape")
+    self._dp_targets = targets
+    self._dp_target_desc = None
+
+  def _scatter_dp_grads(self, bf16: bool):
+    """Local-batch gradient of every replicated table into its persistent target (one launch)."""
+    if not len(self.ddesc_np):
+      return
+    key = (self._key, tuple(t.data_ptr() for t in self._dp_targets))
+    if self._dp_target_desc is None or self._dp_target_desc[0] != key:
+      d = self.ddesc_np.copy()
+      for j in range(len(d)):
+        d[j]["table"] = self._dp_targets[int(d[j]["local_table"])].data_ptr()
+      self._dp_target_desc = (key, _native.upload_struct_array(d, self.device), len(d))
+    _, dd, n = self._dp_target_desc
+    self.ops.scatter_add_bwd(dd, n, self.lb, self.lb, self.lb, self.total_width, [],
+                             [self.grad.data_ptr()], 0, 1.0, 0, self.ids64, bf16, self.vec4, False)
+
   def backward_inplace(self):
     """Backward when the gradient was already written into ``self.grad`` (e.g. by the fused
-    interaction-backward kernel): barrier + fused table update, nothing else."""
+    interaction-backward kernel): barrier + fused table update; replicated tables accumulate
+    their dense gradient into the targets given to :meth:`set_dp_grad_targets`."""
+    bf16 = self.compute_dtype == torch.bfloat16
     if self.W > 1:
       self.ctx.barrier(2)
     if len(self.de.dp_layers):
-      raise RuntimeError("backward_inplace does not handle replicated tables")
-    self._backward_mp(self.compute_dtype == torch.bfloat16)
+      if getattr(self, "_dp_targets", None) is None:
+        raise RuntimeError("backward_inplace needs set_dp_grad_targets() for replicated tables")
+      self._scatter_dp_grads(bf16)
+    self._backward_mp(bf16)
 
   def _backward_mp(self, bf16: bool) -> List[Optional[torch.Tensor]]:
     with nvtx.range("emb_backward_update"):

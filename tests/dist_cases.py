@@ -424,7 +424,11 @@ def case_dlrm_fast_step(rank, world, device, backend, optimizer="sgd", steps=2, 
   ref = DLRM(sizes, device=device, compute_dtype=torch.bfloat16, backend="fused", world_size=1,
              rank=0)
   torch.manual_seed(7)
-  test = DLRM(sizes, device=device, compute_dtype=torch.bfloat16, backend="fused")
+  # dp_threshold: replicate the small tables (their update then rides on the dense SGD kernel)
+  test = DLRM(sizes, device=device, compute_dtype=torch.bfloat16, backend="fused",
+              data_parallel_threshold=kw.get("dp_threshold"))
+  if kw.get("dp_threshold") and world > 1:
+    assert len(test.embedding.dp_layers) > 0
   test.load_state_dict({k: v for k, v in ref.state_dict().items() if "embedding" not in k},
                        strict=False)
   test.embedding.set_weights(ref.embedding.get_weights(all_ranks=True))

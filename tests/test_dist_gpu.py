@@ -92,3 +92,13 @@ def test_subgroups_fused():
   if torch.cuda.device_count() < 4:
     pytest.skip("needs 4 GPUs")
   launch("case_subgroups", world=4, device_type="cuda", backend="fused")
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.skipif(not _EXPERIMENTAL, reason="replicated tables in the fast DLRM step: added "
+                    "after the round-1 GPU budget was spent; set DE_B200_TEST_EXPERIMENTAL=1")
+def test_dlrm_fast_world2_replicated_tables():
+  # tables have 200..525 rows x 128: replicate those up to 300 rows
+  launch("case_dlrm_fast_step", world=2, device_type="cuda", backend="fused", optimizer="sgd",
+         dp_threshold=300 * 128)

@@ -394,3 +394,55 @@ def test_tiny_table_split_path(world, monkeypatch):
   outcomes = [run_plan(8800 * world + s, world, "sgd") for s in range(8)]
   assert outcomes.count("ok") >= 5, outcomes
   assert seen["tiny"] > 0 and seen["main"] > seen["tiny"]  # tiny calls main once internally
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_backward_inplace_with_replicated_tables(world):
+  """The hand-scheduled step's path: gradient already in the engine's buffer, replicated tables
+  accumulate their local-batch dense gradient into persistent targets (later all-reduced with
+  the dense parameters), model-parallel tables are updated in place."""
+  rng = np.random.default_rng(77 + world)
+  sizes = [(6, 8), (40, 8), (9, 16), (300, 16), (25, 8), (500, 8)]
+  embs = [{"input_dim": r, "output_dim": w, "combiner": None} for r, w in sizes]
+  kw = {"strategy": "memory_balanced", "data_parallel_threshold": 150} if world > 1 else {}
+  sim, des = dry_run.build_engines(embs, world, **kw)
+  tables = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+  lr, lb = 0.25, 6
+  B = lb * world
+  for de in des:
+    de.set_weights(tables)
+    de.set_optimizer("sgd", lr=lr)
+  dp_tables = des[0].strategy.table_groups[0]
+  assert (len(dp_tables) > 0) == (world > 1)
+  targets = [[torch.zeros(sizes[t]) for t in dp_tables] for _ in range(world)]
+  for r, de in enumerate(des):
+    de._engine.set_dp_grad_targets(targets[r])
+  ids = [rng.integers(0, r_, size=B) for r_, _ in sizes]
+  grads = [rng.standard_normal((B, w)).astype(np.float32) * 0.1 for _, w in sizes]
+
+  def rank_fn(r):
+    de, eng = des[r], des[r]._engine
+    sl = slice(r * lb, (r + 1) * lb)
+    with torch.no_grad():
+      out = de([torch.from_numpy(i[sl]) for i in ids], concat=True)
+      exp = np.concatenate([tables[t][ids[t][sl]] for t in range(len(sizes))], 1)
+      np.testing.assert_allclose(out.numpy(), exp, rtol=1e-5, atol=1e-5)
+      eng.grad.copy_(torch.from_numpy(np.concatenate([g[sl] for g in grads], 1)))
+      eng.backward_inplace()
+
+  dry_run.run_ranks(sim, rank_fn)
+  got = assemble(des)
+  for t, (rows, _) in enumerate(sizes):
+    dense = np.zeros_like(tables[t])
+    np.add.at(dense, ids[t], grads[t])
+    if t in dp_tables:
+      np.testing.assert_array_equal(got[t], tables[t])  # applied later, with the dense params
+      j = dp_tables.index(t)
+      for r in range(world):
+        loc = np.zeros_like(tables[t])
+        np.add.at(loc, ids[t][r * lb:(r + 1) * lb], grads[t][r * lb:(r + 1) * lb])
+        np.testing.assert_allclose(targets[r][j].numpy(), loc, rtol=1e-5, atol=1e-6)
+    else:
+      np.testing.assert_allclose(got[t], tables[t] - lr * dense / world, rtol=1e-5, atol=1e-5)
+  with pytest.raises(ValueError):
+    des[0]._engine.set_dp_grad_targets([torch.zeros(1)] * (len(dp_tables) + 1))

@@ -47,3 +47,7 @@ timeout 300 python bench.py --steps 50 --warmup 10 | tail -1 | tee -a $O/summary
 #   for C in 4 2 1; do DE_B200_EMB_BLOCKS_PER_SM=$C python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
 #     --master-addr 127.0.0.1 --master-port 2967$C bench.py --gpus 8 --steps 50 --warmup 10 --no-e2e | tail -1; done
 #   then the same with DE_B200_VEC8_PULL=1
+# 8. (2 GPUs, then 8) replicated tiny tables in the fast step: numerics, then the headline with them
+#   DE_B200_TEST_EXPERIMENTAL=1 python -m pytest tests/test_dist_gpu.py -q -x -k replicated_tables
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29680 \
+#     bench.py --gpus 8 --steps 50 --warmup 10 --no-e2e --data-parallel-threshold 300000 | tail -1
