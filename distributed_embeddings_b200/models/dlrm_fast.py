@@ -137,6 +137,7 @@ class DLRMTrainStep:
       if self._dp_slots:
         self.engine.set_dp_grad_targets(dp_targets)
         self.engine._tables_dirty = True
+        self.engine._key = None  # descriptors built earlier point at the old table storage
       for L in layers:
         wv = self.p32[L.w_off:L.w_off + L.w_numel].view(L.out_f, L.in_pad)
         wv[:, :L.in_f].copy_(L.lin.weight)
