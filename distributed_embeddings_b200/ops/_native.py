@@ -81,7 +81,7 @@ def available() -> bool:
 
 # number of kernels each native op launches (for the benchmark's launch accounting)
 _KERNELS_PER_OP = {
-    "lookup_fwd": 1, "scatter_add_bwd": 1, "tiny_scatter_add_bwd": 1, "sort_items": 12, "segment_update": 1,
+    "lookup_fwd": 1, "lookup_fwd_bulk": 1, "scatter_add_bwd": 1, "tiny_scatter_add_bwd": 1, "sort_items": 12, "segment_update": 1,
     "embedding_lookup_fwd": 1, "embedding_scatter_add": 1, "embedding_lookup_grad": 14,
     "row_to_split": 1, "hash_init": 1, "integer_lookup": 1, "barrier": 1, "allreduce": 1,
     "gather_segments": 1, "gather_ragged": 1, "copy_cast_2d": 1, "dense_sgd": 1, "interact_fwd": 1, "interact_bwd": 1,

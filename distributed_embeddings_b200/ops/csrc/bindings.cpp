@@ -83,6 +83,19 @@ void scatter_add_bwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64
   check_launch();
 }
 
+void lookup_fwd_bulk(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
+                     int64_t dst_batch, int64_t dst_stride, at::IntArrayRef src_ptrs,
+                     at::IntArrayRef dst_ptrs, int64_t rot, bool ids64, bool out_bf16) {
+  TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
+  c10::cuda::CUDAGuard guard(descs.device());
+  bool ok = de::launch_lookup_fwd_bulk(
+      reinterpret_cast<const de::InputDesc*>(descs.data_ptr()), static_cast<int>(n_inputs), batch,
+      src_batch, dst_batch, dst_stride, to_peers(src_ptrs), to_peers(dst_ptrs),
+      static_cast<int>(rot), ids64, out_bf16, sm_count(), cur_stream());
+  TORCH_CHECK(ok, "lookup_fwd_bulk: launch failure");
+  check_launch();
+}
+
 void tiny_scatter_add_bwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
                           int64_t grad_batch, int64_t grad_stride, at::IntArrayRef src_ptrs,
                           at::IntArrayRef grad_ptrs, double scale, int64_t scale_ptr, bool ids64,
@@ -730,6 +743,10 @@ TORCH_LIBRARY(de_b200, m) {
       "int grad_stride, int[] src_ptrs, int[] grad_ptrs, int rot, float scale, int scale_ptr, bool ids64, "
       "bool grad_bf16, bool vec4, bool vec8) -> ()",
       &scatter_add_bwd);
+  m.def(
+      "lookup_fwd_bulk(Tensor descs, int n_inputs, int batch, int src_batch, int dst_batch, "
+      "int dst_stride, int[] src_ptrs, int[] dst_ptrs, int rot, bool ids64, bool out_bf16) -> ()",
+      &lookup_fwd_bulk);
   m.def(
       "tiny_scatter_add_bwd(Tensor descs, int n_inputs, int batch, int src_batch, int grad_batch, "
       "int grad_stride, int[] src_ptrs, int[] grad_ptrs, float scale, int scale_ptr, bool ids64, "

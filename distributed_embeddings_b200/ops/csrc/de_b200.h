@@ -72,6 +72,12 @@ void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch,
                             bool ids64, bool grad_bf16, bool vec4, int sm_count,
                             cudaStream_t stream, bool vec8 = false);
 
+// one-hot forward through TMA bulk row copies (experimental, see lookup_kernels.cu)
+bool launch_lookup_fwd_bulk(const InputDesc* descs, int n_inputs, int64_t batch,
+                            int64_t src_batch, int64_t dst_batch, int64_t dst_stride,
+                            const PeerPtrs& src, const PeerPtrs& dst, int rot, bool ids64,
+                            bool out_bf16, int sm_count, cudaStream_t stream);
+
 // tiny one-hot tables: shared-memory pre-reduction (see lookup_kernels.cu)
 bool launch_tiny_scatter_add(const InputDesc* descs, int n_inputs, int64_t batch,
                              int64_t src_batch, int64_t grad_batch, int64_t grad_stride,

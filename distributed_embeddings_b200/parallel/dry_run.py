@@ -257,6 +257,18 @@ class DryOps:
         else:
           view.copy_(pooled.to(odt))
 
+  def lookup_fwd_bulk(self, descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src_ptrs,
+                      dst_ptrs, rot, ids64, out_bf16):
+    """TMA bulk-copy variant: same contract, restricted to one-hot rows of <= 128 columns whose
+    16-byte pieces are aligned (what the engine must have checked before choosing it)."""
+    for d in self._descs(descs, n_inputs):
+      assert int(d["hotness"]) == 1 and not int(d["offsets"]) and not int(d["flags"])
+      assert int(d["width"]) % 4 == 0 and int(d["width"]) <= 128 and int(d["dst_col"]) % 4 == 0
+      assert int(d["table"]) % 16 == 0 and dst_stride % 4 == 0
+    self.lookup_fwd(descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src_ptrs, dst_ptrs,
+                    rot, ids64, out_bf16, True)
+    self.calls["lookup_fwd_bulk"] = self.calls.get("lookup_fwd_bulk", 0) + 1
+
   # -- index exchange ------------------------------------------------------------------------
   def gather_segments(self, segs, src_ptrs, dst, max_seg):
     self._count("gather_segments")

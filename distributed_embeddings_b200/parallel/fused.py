@@ -347,6 +347,16 @@ class FusedEngine:
         not len(row_inputs)
     # shared-memory pre-reduction of tiny one-hot tables in the SGD backward (experimental)
     self.tiny_tables = os.environ.get("DE_B200_TINY_TABLES", "0") == "1"
+    # TMA bulk row copies for one-hot table-parallel / replicated lookups (experimental):
+    # every input one id per sample, rows of at most 128 fp32 columns, 16-byte aligned pieces
+    def bulk_ok(desc):
+      return len(desc) > 0 and bool(np.all(desc["hotness"] == 1)) and \
+          bool(np.all(desc["offsets"] == 0)) and bool(np.all(desc["width"] % 4 == 0)) and \
+          bool(np.all(desc["width"] <= 128)) and bool(np.all(desc["dst_col"] % 4 == 0)) and \
+          bool(np.all(desc["flags"] == 0))
+    bulk = os.environ.get("DE_B200_LOOKUP_BULK", "0") == "1" and tw % 4 == 0
+    self.bulk_c = bulk and bulk_ok(cdesc)
+    self.bulk_d = bulk and bulk_ok(ddesc)
     self._upload()
     self._key = (b, hots, ids64)
 
@@ -515,11 +525,19 @@ class FusedEngine:
         ops.gather_ragged(self.rsegs, self.in_ptrs, self.split_ptrs, self.ids_mp, self.goff,
                           self.lb, self.max_rcap)
     if self.ddesc is not None:
-      ops.lookup_fwd(self.ddesc, len(self.ddesc_np), lb, lb, lb, self.total_width, [],
-                     [self.out.data_ptr()], 0, self.ids64, bf16, self.vec4)
+      if self.bulk_d:
+        ops.lookup_fwd_bulk(self.ddesc, len(self.ddesc_np), lb, lb, lb, self.total_width, [],
+                            [self.out.data_ptr()], 0, self.ids64, bf16)
+      else:
+        ops.lookup_fwd(self.ddesc, len(self.ddesc_np), lb, lb, lb, self.total_width, [],
+                       [self.out.data_ptr()], 0, self.ids64, bf16, self.vec4)
     if self.cdesc is not None:
-      ops.lookup_fwd(self.cdesc, len(self.cdesc_np), B, B, lb, self.total_width, [],
-                     self.out_ptrs, rank, self.ids64, bf16, self.vec4)
+      if self.bulk_c:
+        ops.lookup_fwd_bulk(self.cdesc, len(self.cdesc_np), B, B, lb, self.total_width, [],
+                            self.out_ptrs, rank, self.ids64, bf16)
+      else:
+        ops.lookup_fwd(self.cdesc, len(self.cdesc_np), B, B, lb, self.total_width, [],
+                       self.out_ptrs, rank, self.ids64, bf16, self.vec4)
     if self.rdesc is not None:
       ops.lookup_fwd(self.rdesc, len(self.rdesc_np), B, B, lb, self.rs_width, [], self.rs_ptrs,
                      rank, self.ids64, False, self.vec4)

@@ -102,3 +102,17 @@ def test_dlrm_fast_world2_replicated_tables():
   # tables have 200..525 rows x 128: replicate those up to 300 rows
   launch("case_dlrm_fast_step", world=2, device_type="cuda", backend="fused", optimizer="sgd",
          dp_threshold=300 * 128)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _EXPERIMENTAL, reason="TMA bulk-copy forward (DE_B200_LOOKUP_BULK=1): added "
+                    "after the round-1 GPU budget was spent; set DE_B200_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("case", ["case_basic", "case_memory_balanced", "case_shared_dp",
+                                  "case_column_slice_threshold", "case_int32_ids",
+                                  "case_data_parallel", "case_fuzz"])
+def test_fused_bulk_lookup(case, world, monkeypatch):
+  if torch.cuda.device_count() < world:
+    pytest.skip(f"needs {world} GPUs")
+  monkeypatch.setenv("DE_B200_LOOKUP_BULK", "1")  # inherited by the spawned ranks
+  launch(case, world=world, device_type="cuda", backend="fused")

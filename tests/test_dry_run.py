@@ -500,3 +500,29 @@ def test_optimizer_state_checkpoint_resume(kind):
   sim_d, des_d = make(saved_w)
   step(sim_d, des_d, batches[1])
   assert any(not np.allclose(a, b, rtol=1e-5, atol=1e-6) for a, b in zip(straight, assemble(des_d)))
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_bulk_lookup_selection(world, monkeypatch):
+  """DE_B200_LOOKUP_BULK=1: the TMA bulk-copy forward is chosen only when every descriptor of a
+  launch qualifies (one id per sample, <= 128 aligned columns), and the plan still computes the
+  right thing through it."""
+  monkeypatch.setenv("DE_B200_LOOKUP_BULK", "1")
+  used = {"bulk": 0, "plain": 0}
+  orig = dry_run.build_engines
+  last = {}
+
+  def spy(embs, w, **kw):
+    sim, des = orig(embs, w, **kw)
+    last["des"] = des
+    return sim, des
+
+  monkeypatch.setattr(dry_run, "build_engines", spy)
+  for s in range(10):
+    if run_plan(6100 * world + s, world, "sgd") != "ok":
+      continue
+    for de in last["des"]:
+      c = de._engine.ops.calls
+      used["bulk"] += c.get("lookup_fwd_bulk", 0)
+      used["plain"] += c.get("lookup_fwd", 0) - c.get("lookup_fwd_bulk", 0)
+  assert used["bulk"] > 0 and used["plain"] > 0, used

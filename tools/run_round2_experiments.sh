@@ -31,6 +31,11 @@ DE_B200_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_dense_kernel
 echo "interact v2 test rc=$?" | tee -a $O/summary.txt
 DE_B200_INTERACT_V2=1 timeout 200 python tools/profile_step.py --model dlrm-mlperf --out $O/step_mlperf_interact_v2.txt > /dev/null 2>&1
 grep -h "interact_bwd" $O/step_mlperf.txt $O/step_mlperf_interact_v2.txt | tee -a $O/summary.txt
+# 3c. TMA bulk-copy forward: numerics (1 GPU), then the lookup kernel time with it
+DE_B200_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_dist_gpu.py -x -q -k "bulk_lookup and 1-" > $O/bulk_lookup_test.log 2>&1
+echo "bulk lookup test rc=$?" | tee -a $O/summary.txt
+DE_B200_LOOKUP_BULK=1 timeout 200 python tools/profile_step.py --model dlrm-mlperf --out $O/step_mlperf_bulk.txt > /dev/null 2>&1
+grep -h "lookup_fwd" $O/step_mlperf.txt $O/step_mlperf_bulk.txt | tee -a $O/summary.txt
 # 4. headline
 timeout 300 python bench.py --steps 50 --warmup 10 | tail -1 | tee -a $O/summary.txt
 
