@@ -58,6 +58,8 @@ def reference_step(tables, imap, glob_ids, combiners, grads, lr, world, kind, st
       out = np.zeros((len(ids), tables[t].shape[1]), dtype=np.float32)
       for b, row in enumerate(ids):
         n = len(row)
+        if n == 0:
+          continue
         scale = 1.0 / n if combiners[t] == "mean" else 1.0
         out[b] = tables[t][row].sum(0) * scale
         np.add.at(dense[t], np.asarray(row, dtype=np.int64), grads[i][b] * scale)
@@ -138,7 +140,8 @@ def run_plan(seed, world, kind="sgd", dtype=torch.float32, ragged=False):
   rag = [ragged and rng.random() < 0.6 for _ in imap]
   for i, t in enumerate(imap):
     if rag[i]:
-      glob[i] = [list(nrng.integers(0, sizes[t][0], size=rng.randint(1, 4))) for _ in range(B)]
+      # 0 ids is legal: the sample pools to zero and contributes no gradient
+      glob[i] = [list(nrng.integers(0, sizes[t][0], size=rng.randint(0, 4))) for _ in range(B)]
   if ragged:
     for de in des:
       de.ragged_capacity = 4
