@@ -62,6 +62,12 @@ def parse_args():
   p.add_argument("--trainer", default="fast", choices=["fast", "autograd"],
                  help="fast = hand-scheduled step + CUDA graph (DLRMTrainStep); autograd = "
                       "nn.Module + HybridTrainer")
+  p.add_argument("--alpha", type=float, default=0.0,
+                 help="power-law exponent of the synthetic ids (0 = uniform; the reference's "
+                      "synthetic benchmark uses 1.05)")
+  p.add_argument("--no-verify", action="store_true",
+                 help="skip the pre-flight numerics check (2 steps of a 1/1000-rows plan on all "
+                      "ranks vs a single-process fp32 PyTorch oracle on rank 0)")
   return p.parse_args()
 
 
@@ -143,10 +149,20 @@ class ClockSampler:
             "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# Criteo Terabyte cardinalities without the MLPerf 40 M cap (882 M rows, 421 GiB at dim 128 fp32:
+# only fits sharded over 8 GPUs) - BASELINE.json's "~800M rows total" configuration
+CRITEO_1TB_FULL_SIZES = [
+    227605432, 39060, 17295, 7424, 20265, 3, 7122, 1543, 63, 130229467, 3067956, 405282, 10, 2209,
+    11938, 155, 4, 976, 14, 292775614, 40790948, 187188510, 590152, 12973, 108, 36
+]
+
+
 def table_sizes_for(model: str):
   from distributed_embeddings_b200.models.dlrm import mlperf_table_sizes
   if model == "dlrm-mlperf":
     return mlperf_table_sizes()
+  if model == "dlrm-full":
+    return [s + 1 for s in CRITEO_1TB_FULL_SIZES]
   if model == "dlrm-small":
     return 26 * [100000]
   if model == "dlrm-tiny":
@@ -171,6 +187,124 @@ def auto_column_slice_threshold(sizes, dim, world):
     if best_cols is None or cols < best_cols:
       best, best_cols = thr, cols
   return best
+
+
+def gen_ids(rows: int, n: int, alpha: float, gen):
+  """Synthetic categorical ids: uniform, or the reference generator's power law (alpha > 0)."""
+  import torch
+  if alpha <= 0:
+    return torch.randint(0, rows, (n,), generator=gen, dtype=torch.int32)
+  r = torch.rand(n, generator=gen, dtype=torch.float64)
+  g = 1.0 - alpha
+  y = (r * ((rows + 1.0)**g - 1.0) + 1.0)**(1.0 / g)
+  return (y.to(torch.int64) - 1).clamp_(0, rows - 1).to(torch.int32)
+
+
+def verify(args, device, world, rank, compute_dtype, cst_for):
+  """Pre-flight numerics check that the driver can see at every N: two training steps of a
+  scaled-down plan (same 26 tables / MLPs / sharding knobs, 1/1000 of the rows) through the
+  benchmarked trainer on all ranks, against a single-process fp32 PyTorch oracle on rank 0 that
+  shares nothing with this framework but the initial weights (plain indexing, bmm interaction,
+  nn.functional linear layers, autograd, in-place SGD)."""
+  import torch
+  import torch.distributed as dist
+  from distributed_embeddings_b200.models.dlrm import DLRM
+
+  sizes = [max(4, s // 1000) for s in table_sizes_for(args.model)]
+  gbv, lr = 256 * world, 1.0
+  lbv = gbv // world
+  torch.manual_seed(4321)
+  cst = cst_for(sizes)
+  model = DLRM(sizes, device=device, compute_dtype=compute_dtype, backend=args.backend,
+               column_slice_threshold=cst, data_parallel_threshold=None)
+  from distributed_embeddings_b200 import broadcast_variables
+  broadcast_variables(model)
+  # oracle copy of the initial state (rank 0 holds the global tables)
+  w0 = model.embedding.get_weights()
+  dense0 = [(m.weight.detach().float().clone(), m.bias.detach().float().clone())
+            for m in list(model.bottom_mlp.net) + list(model.top_mlp.net)
+            if isinstance(m, torch.nn.Linear)]
+  n_bottom = sum(isinstance(m, torch.nn.Linear) for m in model.bottom_mlp.net)
+  if args.trainer == "fast" and args.backend == "fused":
+    from distributed_embeddings_b200.models.dlrm_fast import DLRMTrainStep
+    trainer = DLRMTrainStep(model, lr=lr, embedding_optimizer="sgd",
+                            use_cuda_graph=bool(args.cuda_graph), gemm=args.gemm)
+  else:
+    from distributed_embeddings_b200.models.trainer import HybridTrainer
+    trainer = HybridTrainer(model, lr=lr, embedding_optimizer="sgd")
+  g = torch.Generator().manual_seed(7 + rank)
+  batches, losses = [], []
+  for _ in range(2):
+    num = torch.rand(lbv, 13, generator=g)
+    cat = torch.stack([gen_ids(s, lbv, args.alpha, g) for s in sizes])
+    lab = torch.randint(0, 2, (lbv, 1), generator=g).float()
+    batches.append((num.to(device), cat.to(device), lab.to(device)))
+  for num, cat, lab in batches:
+    if args.trainer == "fast" and args.backend == "fused":
+      loss = trainer.step(num, cat, lab)
+    else:
+      loss = trainer.step(num, list(cat.unbind(0)), lab)
+    loss = loss.detach().float().reshape(1).clone()
+    if world > 1:
+      dist.all_reduce(loss)
+      loss /= world
+    losses.append(float(loss.item()))
+  w1 = model.embedding.get_weights()
+  # global batches on rank 0
+  glob = []
+  for num, cat, lab in batches:
+    if world > 1:
+      parts = [[torch.empty_like(t) for _ in range(world)] for t in (num, cat, lab)]
+      for p, t in zip(parts, (num, cat, lab)):
+        dist.all_gather(p, t.contiguous())
+      glob.append((torch.cat(parts[0]), torch.cat(parts[1], dim=1), torch.cat(parts[2])))
+    else:
+      glob.append((num, cat, lab))
+  result = None
+  if rank == 0:
+    tabs = [torch.from_numpy(w).to(device).requires_grad_(True) for w in w0]
+    dense = [(w.clone().requires_grad_(True), b.clone().requires_grad_(True)) for w, b in dense0]
+    params = tabs + [t for wb in dense for t in wb]
+    n = len(sizes) + 1
+    ii, jj = torch.tril_indices(n, n, offset=-1)
+    ii, jj = ii.to(device), jj.to(device)
+    olosses = []
+    for num, cat, lab in glob:
+      x = num
+      for i, (w, b) in enumerate(dense[:n_bottom]):
+        x = torch.relu(torch.nn.functional.linear(x, w, b))
+      feats = torch.stack([x] + [tabs[t][cat[t].long()] for t in range(len(sizes))], dim=1)
+      z = torch.bmm(feats, feats.transpose(1, 2))[:, ii, jj]
+      h = torch.cat([z, x], dim=1)
+      top = dense[n_bottom:]
+      for i, (w, b) in enumerate(top):
+        h = torch.nn.functional.linear(h, w, b)
+        if i < len(top) - 1:
+          h = torch.relu(h)
+      loss = torch.nn.functional.binary_cross_entropy_with_logits(h, lab)
+      olosses.append(float(loss.item()))
+      grads = torch.autograd.grad(loss, params)
+      with torch.no_grad():
+        for p, gr in zip(params, grads):
+          p -= lr * gr
+    max_err, max_upd = 0.0, 0.0
+    for t in range(len(sizes)):
+      got = torch.from_numpy(w1[t]).to(device)
+      max_err = max(max_err, float((got - tabs[t].detach()).abs().max()))
+      max_upd = max(max_upd, float((tabs[t].detach() - torch.from_numpy(w0[t]).to(device)).abs().max()))
+    loss_err = max(abs(a - b) for a, b in zip(losses, olosses))
+    tol = 0.05 * max_upd + 1e-4
+    result = {"max_abs_err": max_err, "max_update": max_upd, "tolerance": tol,
+              "loss": losses, "oracle_loss": olosses, "loss_abs_err": loss_err,
+              "tables_rows": int(sum(sizes)), "global_batch": gbv, "steps": 2,
+              "oracle": "single-process fp32 PyTorch (rank 0)",
+              "ok": bool(max_err <= tol and loss_err <= 3e-2 and max_upd > 0)}
+  flag = torch.tensor([1 if (result is None or result["ok"]) else 0], device=device)
+  if world > 1:
+    dist.broadcast(flag, src=0)
+  del trainer, model
+  torch.cuda.empty_cache()
+  return result, bool(flag.item())
 
 
 def main():
@@ -209,17 +343,43 @@ def main():
     cst = None
   else:
     cst = int(cst)
+  verify_result, verify_ok = None, True
+  if not args.no_verify:
+    raw_cst = args.column_slice_threshold
+
+    def cst_for(vsizes):
+      if raw_cst == "auto":
+        return auto_column_slice_threshold(vsizes, 128, world)
+      if raw_cst is None or str(raw_cst).lower() == "none":
+        return None
+      return max(1, int(raw_cst) // 1000)
+    verify_result, verify_ok = verify(args, device, world, rank, compute_dtype, cst_for)
+    if not verify_ok:
+      if rank == 0:
+        print(json.dumps({"verify": verify_result, "error": "numerics check failed"}))
+      if world > 1:
+        dist.destroy_process_group()
+      return 3
+  torch.manual_seed(1234)
   model = DLRM(sizes, device=device, compute_dtype=compute_dtype, backend=args.backend,
                column_slice_threshold=cst, data_parallel_threshold=args.data_parallel_threshold)
   from distributed_embeddings_b200 import broadcast_variables
   broadcast_variables(model)
   use_fast = args.trainer == "fast" and args.backend == "fused"
+  # the reference's schedule (examples/dlrm/main.py:192-197): SGD lr 24 reached after 8000
+  # warm-up steps, polynomial decay from step 48000; the learning rate lives in device memory so
+  # the captured step follows it
+  from distributed_embeddings_b200.utils.lr_schedule import LearningRateScheduler
+  scheduler = LearningRateScheduler(args.lr, warmup_steps=8000, decay_start_step=48000,
+                                    decay_steps=24000)
   if use_fast:
     from distributed_embeddings_b200.models.dlrm_fast import DLRMTrainStep
     trainer = DLRMTrainStep(model, lr=args.lr, embedding_optimizer=args.optimizer,
-                            use_cuda_graph=bool(args.cuda_graph), gemm=args.gemm)
+                            use_cuda_graph=bool(args.cuda_graph), gemm=args.gemm,
+                            scheduler=scheduler)
   else:
-    trainer = HybridTrainer(model, lr=args.lr, embedding_optimizer=args.optimizer)
+    trainer = HybridTrainer(model, lr=args.lr, embedding_optimizer=args.optimizer,
+                            scheduler=scheduler)
 
   # ---- synthetic Criteo-shaped data in pinned host memory (uniform ids, random-init tables)
   n_feat = len(sizes)
@@ -227,7 +387,7 @@ def main():
   pool = []
   for _ in range(args.data_batches):
     num = torch.rand(lb, 13, generator=g).pin_memory()
-    cat = torch.stack([torch.randint(0, s, (lb,), generator=g, dtype=torch.int32)
+    cat = torch.stack([gen_ids(s, lb, args.alpha, g)
                        for s in sizes]).pin_memory()  # [26, lb] feature major = staging layout
     lab = torch.randint(0, 2, (lb, 1), generator=g).float().pin_memory()
     pool.append((num, cat, lab))
@@ -329,6 +489,19 @@ def main():
     launches = _native.launch_count() * args.steps
     torch.cuda.synchronize()
   clocks = sampler.stop() if rank == 0 else None
+  # the timed steps trained for real: the last loss must be a finite number
+  final_loss = step_from_device(0).detach().float().reshape(1).clone()
+  if world > 1:
+    dist.all_reduce(final_loss)
+    final_loss /= world
+  final_loss = float(final_loss.item())
+  if final_loss != final_loss or abs(final_loss) == float("inf"):
+    if rank == 0:
+      print(json.dumps({"error": "training diverged: non-finite loss after the timed steps",
+                        "final_loss": str(final_loss)}))
+    if world > 1:
+      dist.destroy_process_group()
+    return 4
 
   if args.profile:
     from torch.profiler import ProfilerActivity, profile
@@ -389,7 +562,8 @@ def main():
         "scaling": "strong",
         "vs_baseline": value / BASELINE_SAMPLES_PER_SEC,
         "dtype": args.dtype,
-        "data": "synthetic (uniform Criteo-shaped ids, random-init tables)",
+        "data": "synthetic (" + ("uniform" if args.alpha <= 0 else f"power-law alpha={args.alpha}") +
+                " Criteo-shaped ids, random-init tables)",
         "impl": "b200",
         "config": {
             "model": f"DLRM {args.model}: 26 tables dim 128 ({sum(sizes)} rows, "
@@ -398,13 +572,17 @@ def main():
             "seq_len": 1,
             "parallelism": f"hybrid: dp{world} dense + table-parallel embeddings "
                            f"(memory_balanced, column_slice_threshold={cst}), backend={args.backend}, trainer={args.trainer}, cuda_graph={int(bool(args.cuda_graph))}, mlp_gemm={args.gemm}, dense_allreduce={getattr(trainer, 'allreduce_kind', 'torch')}",
-            "optimizer": f"{args.optimizer} lr={args.lr} (embedding update fused in backward)",
+            "optimizer": f"{args.optimizer} lr={args.lr}, warm-up 8000 / decay from 48000 steps "
+                         "like the reference (embedding update fused in backward)",
             "l2_policy": "inputs larger than L2: random rows of "
                          f"{table_gb / world:.1f} GiB tables per GPU vs 126 MB L2",
         },
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": launches,
+        "final_loss": final_loss,
+        "e2e_final_loss": e2e_losses[-1] if e2e_losses else None,
+        "verify": verify_result,
     }
     print(json.dumps(out))
   if world > 1:

@@ -104,6 +104,8 @@ class DLRM(nn.Module):
                                           backend=backend,
                                           world_size=world_size,
                                           rank=rank)
+    # the activation is consumed inside this module's step: no defensive copy of the engine buffer
+    self.embedding.zero_copy_output = True
     ii, jj = torch.tril_indices(n, n, offset=-1)
     self.register_buffer("tril", (ii * n + jj).to(device), persistent=False)
 

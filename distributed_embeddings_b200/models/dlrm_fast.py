@@ -10,8 +10,9 @@ math as one static schedule over preallocated buffers:
 * MLP layers: cuBLASLt bf16 GEMMs with fused bias+ReLU epilogues forward, plain GEMMs backward
   (K padded 13->16 and 479->480 so the tcgen05 library kernels are eligible), fused
   ReLU-backward+bias-gradient kernel;
-* dot interaction forward/backward: tensor-core kernels; the backward writes the embedding
-  gradient directly into the embedding engine's symmetric gradient buffer;
+* dot interaction forward/backward: tensor-core kernels; the forward's head waits for the
+  embedding owners' "output ready" signals, the backward pushes every piece of the embedding
+  gradient straight into its owner's receive buffer over NVLink and signals "gradient ready";
 * final layer + BCE loss + their backward: one kernel;
 * embedding forward/backward: the fused P2P engine (``parallel/fused.py``);
 * the whole step is captured in a CUDA graph and replayed (launch bound otherwise).
@@ -165,13 +166,14 @@ class DLRMTrainStep:
     # GPUs, so it is only enabled for large local batches; DE_B200_WGRAD_STREAM=0/1 overrides)
     self._wgrad_overlap = os.environ.get("DE_B200_WGRAD_STREAM", "auto")
     self._wstream = torch.cuda.Stream(device=dev) if overlap else None
-    # DE_B200_AR_OVERLAP=1: all-reduce the top-MLP + head gradients (93 % of the dense parameters,
-    # complete as soon as the top MLP backward is done) on a third stream while the interaction
-    # backward, the embedding exchange and the bottom MLP backward run; only the small bottom-MLP
-    # bucket is reduced at the end.  Written after the GPU budget of round 1 was spent: opt-in
-    # until the 2-GPU numerics test has run with it.
+    # The top-MLP + head gradients (93 % of the dense parameters, complete as soon as the top MLP
+    # backward is done) are all-reduced on a third stream while the interaction backward, the
+    # embedding exchange and the bottom MLP backward run; only the small bottom-MLP bucket is
+    # reduced at the end.  The overlapped kernel is capped at 32 blocks so that its flag spins
+    # cannot starve the kernels the peers wait for.  DE_B200_AR_OVERLAP=0 restores one all-reduce
+    # at the end of the step.
     self._ar_stream = torch.cuda.Stream(device=dev) if (
-        overlap and self.world > 1 and os.environ.get("DE_B200_AR_OVERLAP", "0") == "1") else None
+        overlap and self.world > 1 and os.environ.get("DE_B200_AR_OVERLAP", "1") == "1") else None
 
   def _refresh_transposes(self):
     """K-major copies of W^T for the dgrad GEMMs (2.4 M elements, a few microseconds)."""
@@ -242,12 +244,14 @@ class DLRMTrainStep:
       a, b_ = self._stage
       ops.select_copy([a[0], a[1], a[2]], [b_[0], b_[1], b_[2]],
                       [self.cat_stage, self.num_in, self.lab_in], self._slot_dev)
-    # the embedding exchange (barrier, id pull, gather + NVLink push, barrier) runs on the side
-    # stream while the bottom MLP runs on the main stream; they meet at the interaction
+    # the embedding exchange (id push, gather + NVLink push of the pooled rows; all signalling
+    # folded into those kernels) runs on the side stream while the bottom MLP runs on the main
+    # stream; they meet at the interaction, whose head waits for the owners' "output ready"
+    eng = self.engine
     if self._side is not None:
       self._side.wait_stream(torch.cuda.current_stream())
       with torch.cuda.stream(self._side):
-        emb = self.engine._run_forward()
+        eng.launch_forward()
     ops.cast_pad(self.num_in, self.x0)
     x = self.x0
     for L in self.bottom:
@@ -255,8 +259,12 @@ class DLRMTrainStep:
     if self._side is not None:
       torch.cuda.current_stream().wait_stream(self._side)
     else:
-      emb = self.engine._run_forward()
-    ops.interact_fwd(x, emb, self.n_emb, self.z)
+      eng.launch_forward()
+    if eng.out_needs_reduce:  # multi-hot row slices: partial pools are summed first
+      eng.wait_output()
+      ops.interact_fwd(x, eng.out, self.n_emb, self.z, [])
+    else:
+      ops.interact_fwd(x, eng.out, self.n_emb, self.z, eng.sync_out_wait())
     x = self.z
     for L in self.top:
       x = self._linear_fwd(L, x)
@@ -288,11 +296,13 @@ class DLRMTrainStep:
       off = self.top[0].w_off  # flat layout: bottom layers | top layers | head
       with torch.cuda.stream(ar):
         self.ctx.allreduce_(self.gsym, self.n_flat - off, torch.float32, scale=1.0 / self.world,
-                            byte_offset=off * 4)
-    # interaction backward: embedding gradient lands in the engine's (symmetric) gradient buffer
+                            byte_offset=off * 4, max_blocks=32)
+    # interaction backward: every piece of the embedding gradient is stored straight into the
+    # receive buffer of the rank that owns the table (slice) - the gradient all-to-all rides on
+    # the kernel's epilogue stores - and its tail signals "gradient ready" to the owners
     hb = self.bottom[-1]
-    ops.interact_bwd(hb.y, eng.out, self.n_emb, self.dz, hb.dy, eng.grad.data_ptr(),
-                     eng.total_width, 1.0)
+    ops.interact_bwd(hb.y, eng.out, self.n_emb, self.dz, hb.dy, 0, 0, 1.0, eng.routes_all,
+                     len(eng.routes_all_np), eng.sync_grad_signal())
     # embedding exchange + fused table update, overlapped with the bottom MLP backward
     if self._side is not None:
       self._side.wait_stream(torch.cuda.current_stream())

@@ -148,6 +148,7 @@ class SyntheticModel(_SyntheticBase):
                                           data_parallel_threshold=data_parallel_threshold,
                                           device=device, compute_dtype=compute_dtype,
                                           backend=backend, input_hotness=list(hots))
+    self.embedding.zero_copy_output = True  # consumed inside this module's step
     total = sum(tables[t][1] for t in imap)
     if self.interact_stride is not None:
       total = -(-total // self.interact_stride)

@@ -47,6 +47,11 @@ class HybridTrainer:
     self.bucket.attach()
     self.opt = torch.optim.SGD(self.dense_params, lr=lr, momentum=momentum,
                                foreach=dev.type == "cuda")
+    # plain SGD keeps its learning rate in device memory: a captured CUDA graph bakes host
+    # scalars in, so a scheduler would otherwise leave the dense lr frozen at its capture-time
+    # value while the embedding lr (device resident as well) keeps changing
+    self.momentum = momentum
+    self.lr_t = torch.full((), float(lr), dtype=torch.float32, device=dev)
     self.loss_fn = loss_fn or nn.BCEWithLogitsLoss()
     # whole-step CUDA graph: the first `graph_warmup_steps` calls run eagerly (real steps), the
     # next call captures forward + backward + all-reduce + optimizer and every call replays it
@@ -63,7 +68,28 @@ class HybridTrainer:
     self.lr = lr
     for g in self.opt.param_groups:
       g["lr"] = lr
+    self.lr_t.fill_(float(lr))
     self.emb.set_learning_rate(lr)
+
+  def _dense_step(self):
+    if self.momentum != 0.0:
+      if self._graph is not None or (self.use_cuda_graph and self.scheduler is not None):
+        raise RuntimeError("momentum SGD keeps its learning rate on the host: it cannot follow a "
+                           "scheduler inside a captured CUDA graph (use momentum=0 or "
+                           "use_cuda_graph=False)")
+      self.opt.step()
+      return
+    params = [p for p in self.dense_params if p.grad is not None]
+    if not params:
+      return
+    with torch.no_grad():
+      grads = [p.grad for p in params]
+      if params[0].is_cuda:
+        upd = torch._foreach_mul(grads, self.lr_t)  # device-resident lr (graph replay safe)
+        torch._foreach_sub_(params, upd)
+      else:
+        for p, g in zip(params, grads):
+          p.sub_(g * self.lr_t)
 
   def step(self, numerical, categorical, labels, staged: bool = False) -> torch.Tensor:
     if self.scheduler is not None:
@@ -101,5 +127,5 @@ class HybridTrainer:
     loss.backward()  # embedding tables are updated inside the backward kernels
     self.bucket.gather_grads_()
     self.bucket.allreduce_(average=True)
-    self.opt.step()
+    self._dense_step()
     return loss.detach()

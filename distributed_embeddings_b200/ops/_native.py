@@ -42,6 +42,18 @@ TABLE_DESC = np.dtype([
     ("pad", "<i4"),
 ])
 
+# mirror of de::GradRoute: one contiguous piece of a requester-side gradient row -> its owner
+GRAD_ROUTE = np.dtype([
+    ("dst", "<u8"),
+    ("dst_stride", "<i8"),
+    ("src_col", "<i4"),
+    ("width", "<i4"),
+    ("dst_col", "<i4"),
+    ("pad", "<i4"),
+])
+SYNC_STATE_WORDS = 64
+DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
 OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_ADAM, OPT_EMIT = 0, 1, 2, 3, 4
 MAX_PEERS = 16
 
@@ -63,9 +75,11 @@ def load(required: bool = False) -> bool:
             "(or `make`) to compile the sm_100a kernels")
       torch.ops.load_library(SO_PATH)
       sizes = list(torch.ops.de_b200.struct_sizes())
-      if sizes[0] != INPUT_DESC.itemsize or sizes[1] != TABLE_DESC.itemsize or sizes[2] != MAX_PEERS:
-        raise RuntimeError(f"descriptor layout mismatch: native {sizes} vs python "
-                           f"{[INPUT_DESC.itemsize, TABLE_DESC.itemsize, MAX_PEERS]}")
+      mine = [INPUT_DESC.itemsize, TABLE_DESC.itemsize, MAX_PEERS, GRAD_ROUTE.itemsize,
+              SYNC_STATE_WORDS]
+      if sizes != mine:
+        raise RuntimeError(f"descriptor layout mismatch: native {sizes} vs python {mine} "
+                           "(stale _C.so? rebuild with python -m distributed_embeddings_b200.ops._build)")
       _loaded = True
       return True
     except Exception as e:  # pylint: disable=broad-except
@@ -81,7 +95,8 @@ def available() -> bool:
 
 # number of kernels each native op launches (for the benchmark's launch accounting)
 _KERNELS_PER_OP = {
-    "lookup_fwd": 1, "lookup_fwd_bulk": 1, "scatter_add_bwd": 1, "tiny_scatter_add_bwd": 1, "sort_items": 12, "segment_update": 1,
+    "lookup_fwd": 1, "scatter_add_bwd": 1, "sort_items": 12, "segment_update": 1,
+    "sync_only": 1, "push_segments": 1, "push_grad": 1, "rowslice_reduce": 1,
     "embedding_lookup_fwd": 1, "embedding_scatter_add": 1, "embedding_lookup_grad": 14,
     "row_to_split": 1, "hash_init": 1, "integer_lookup": 1, "barrier": 1, "allreduce": 1,
     "gather_segments": 1, "gather_ragged": 1, "copy_cast_2d": 1, "dense_sgd": 1, "interact_fwd": 1, "interact_bwd": 1,

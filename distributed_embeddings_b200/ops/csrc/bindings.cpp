@@ -51,63 +51,115 @@ void check_launch() {
   TORCH_CHECK(e == cudaSuccess, "kernel launch failed: ", cudaGetErrorString(e));
 }
 
+// ------------------------------------------------------------------ signalling contexts
+// One per CommContext: the peer-mapped signal pads, this rank's epoch words and the watchdog.
+// Ops take `int[] sync` = {handle, wait_ch, wait_abs_ch, signal_ch, counter_slot} (empty = none).
+struct SyncCtx {
+  de::PeerPtrs flags;
+  uint32_t* state;
+  int* error_flag;
+  unsigned long long timeout;
+  int rank, world;
+};
+std::vector<SyncCtx>& sync_ctxs() {
+  static std::vector<SyncCtx> v;
+  return v;
+}
+std::mutex& sync_mutex() {
+  static std::mutex m;
+  return m;
+}
+
+int64_t sync_ctx_create(at::IntArrayRef flag_ptrs, Tensor state, int64_t rank, int64_t world,
+                        int64_t timeout_cycles, int64_t error_ptr) {
+  TORCH_CHECK(state.is_cuda() && state.scalar_type() == at::kInt && state.is_contiguous() &&
+                  state.numel() >= de::kSyncStateWords,
+              "sync state must be an int32 CUDA tensor of >= ", de::kSyncStateWords, " words");
+  SyncCtx c;
+  c.flags = to_peers(flag_ptrs);
+  c.state = reinterpret_cast<uint32_t*>(state.data_ptr<int>());
+  c.error_flag = reinterpret_cast<int*>(error_ptr);
+  c.timeout = static_cast<unsigned long long>(timeout_cycles);
+  c.rank = static_cast<int>(rank);
+  c.world = static_cast<int>(world);
+  std::lock_guard<std::mutex> lock(sync_mutex());
+  sync_ctxs().push_back(c);
+  return static_cast<int64_t>(sync_ctxs().size()) - 1;
+}
+
+de::SyncArgs to_sync(at::IntArrayRef spec) {
+  de::SyncArgs a = de::no_sync();
+  if (spec.size() == 0) return a;
+  TORCH_CHECK(spec.size() == 5, "sync spec = {handle, wait_ch, wait_abs_ch, signal_ch, slot}");
+  SyncCtx c;
+  {
+    std::lock_guard<std::mutex> lock(sync_mutex());
+    TORCH_CHECK(spec[0] >= 0 && spec[0] < static_cast<int64_t>(sync_ctxs().size()),
+                "unknown sync context");
+    c = sync_ctxs()[spec[0]];
+  }
+  for (int i = 1; i <= 3; ++i)
+    TORCH_CHECK(spec[i] >= -1 && spec[i] < de::kSyncChannels, "sync channel out of range");
+  TORCH_CHECK(spec[4] >= 0 && spec[4] < 2 * de::kSyncChannels, "sync counter slot out of range");
+  a.flags = c.flags;
+  a.state = c.state;
+  a.error_flag = c.error_flag;
+  a.timeout = c.timeout;
+  a.rank = c.rank;
+  a.world = c.world;
+  a.wait_ch = static_cast<int32_t>(spec[1]);
+  a.wait_abs_ch = static_cast<int32_t>(spec[2]);
+  a.signal_ch = static_cast<int32_t>(spec[3]);
+  a.counter_slot = static_cast<int32_t>(spec[4]);
+  return a;
+}
+
+int dtype_code(at::ScalarType t) {
+  if (t == at::kFloat) return 0;
+  if (t == at::kBFloat16) return 1;
+  if (t == at::kHalf) return 2;
+  TORCH_CHECK(false, "activations / gradients must be fp32, bf16 or fp16");
+  return -1;
+}
+
+void sync_only(at::IntArrayRef sync) {
+  de::launch_sync_only(to_sync(sync), cur_stream());
+  check_launch();
+}
+
 // ------------------------------------------------------------------ descriptor-driven ops
 std::vector<int64_t> struct_sizes() {
   return {static_cast<int64_t>(sizeof(de::InputDesc)), static_cast<int64_t>(sizeof(de::TableDesc)),
-          static_cast<int64_t>(de::kMaxPeers)};
+          static_cast<int64_t>(de::kMaxPeers), static_cast<int64_t>(sizeof(de::GradRoute)),
+          static_cast<int64_t>(de::kSyncStateWords)};
 }
 
 void lookup_fwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
                 int64_t dst_batch, int64_t dst_stride, at::IntArrayRef src_ptrs,
-                at::IntArrayRef dst_ptrs, int64_t rot, bool ids64, bool out_bf16, bool vec4) {
+                at::IntArrayRef dst_ptrs, int64_t rot, bool ids64, int64_t act_dtype, bool vec4,
+                at::IntArrayRef sync) {
   TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
   c10::cuda::CUDAGuard guard(descs.device());
   de::launch_lookup_fwd(reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
                         static_cast<int>(n_inputs), batch, src_batch, dst_batch, dst_stride,
                         to_peers(src_ptrs), to_peers(dst_ptrs), static_cast<int>(rot), ids64,
-                        out_bf16, vec4, sm_count(), cur_stream());
+                        static_cast<int>(act_dtype), vec4, sm_count(), cur_stream(),
+                        to_sync(sync));
   check_launch();
 }
 
 void scatter_add_bwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
                      int64_t grad_batch, int64_t grad_stride, at::IntArrayRef src_ptrs,
                      at::IntArrayRef grad_ptrs, int64_t rot, double scale, int64_t scale_ptr,
-                     bool ids64, bool grad_bf16, bool vec4, bool vec8) {
+                     bool ids64, int64_t act_dtype, bool vec4, bool vec8, at::IntArrayRef sync) {
   TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
   c10::cuda::CUDAGuard guard(descs.device());
   de::launch_scatter_add_bwd(reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
                              static_cast<int>(n_inputs), batch, src_batch, grad_batch, grad_stride,
                              to_peers(src_ptrs), to_peers(grad_ptrs), static_cast<int>(rot),
                              static_cast<float>(scale), reinterpret_cast<const float*>(scale_ptr),
-                             ids64, grad_bf16, vec4, sm_count(), cur_stream(), vec8);
-  check_launch();
-}
-
-void lookup_fwd_bulk(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
-                     int64_t dst_batch, int64_t dst_stride, at::IntArrayRef src_ptrs,
-                     at::IntArrayRef dst_ptrs, int64_t rot, bool ids64, bool out_bf16) {
-  TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
-  c10::cuda::CUDAGuard guard(descs.device());
-  bool ok = de::launch_lookup_fwd_bulk(
-      reinterpret_cast<const de::InputDesc*>(descs.data_ptr()), static_cast<int>(n_inputs), batch,
-      src_batch, dst_batch, dst_stride, to_peers(src_ptrs), to_peers(dst_ptrs),
-      static_cast<int>(rot), ids64, out_bf16, sm_count(), cur_stream());
-  TORCH_CHECK(ok, "lookup_fwd_bulk: launch failure");
-  check_launch();
-}
-
-void tiny_scatter_add_bwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
-                          int64_t grad_batch, int64_t grad_stride, at::IntArrayRef src_ptrs,
-                          at::IntArrayRef grad_ptrs, double scale, int64_t scale_ptr, bool ids64,
-                          bool grad_bf16, int64_t max_rows, int64_t max_width) {
-  TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
-  c10::cuda::CUDAGuard guard(descs.device());
-  bool ok = de::launch_tiny_scatter_add(
-      reinterpret_cast<const de::InputDesc*>(descs.data_ptr()), static_cast<int>(n_inputs), batch,
-      src_batch, grad_batch, grad_stride, to_peers(src_ptrs), to_peers(grad_ptrs),
-      static_cast<float>(scale), reinterpret_cast<const float*>(scale_ptr), ids64, grad_bf16,
-      static_cast<int>(max_rows), static_cast<int>(max_width), cur_stream());
-  TORCH_CHECK(ok, "tiny_scatter_add_bwd: unsupported shape or launch failure");
+                             ids64, static_cast<int>(act_dtype), vec4, sm_count(), cur_stream(),
+                             vec8, to_sync(sync));
   check_launch();
 }
 
@@ -179,6 +231,9 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> sort_items(const Tensor& descs, const
                                                       int64_t n_items, int64_t total_rows,
                                                       bool prefill_sentinel) {
   TORCH_CHECK(descs.is_cuda() && tables.is_cuda());
+  // item = input * batch + sample is stored in 32 bits (sparse_update_kernels.cu)
+  TORCH_CHECK(n_inputs * batch < (int64_t(1) << 32),
+              "sorted update: n_inputs * batch = ", n_inputs * batch, " does not fit 32-bit items");
   c10::cuda::CUDAGuard guard(descs.device());
   auto stream = cur_stream();
   auto i64 = at::TensorOptions().device(descs.device()).dtype(at::kLong);
@@ -237,8 +292,8 @@ void segment_update(const Tensor& descs, const Tensor& tables, int64_t n_tables,
                     const Tensor& n_unique, int64_t opt_kind, double lr, double eps, double beta1,
                     double beta2, double bias1, double bias2, double grad_scale,
                     double weight_decay, int64_t lr_ptr, const c10::optional<Tensor>& emit_keys,
-                    const c10::optional<Tensor>& emit_rows, int64_t max_width, bool grad_bf16,
-                    bool vec4, const c10::optional<Tensor>& scratch) {
+                    const c10::optional<Tensor>& emit_rows, int64_t max_width, int64_t act_dtype,
+                    bool vec4, const c10::optional<Tensor>& scratch, int64_t step_ptr) {
   c10::cuda::CUDAGuard guard(descs.device());
   de::OptimizerArgs opt;
   opt.kind = static_cast<int32_t>(opt_kind);
@@ -251,6 +306,7 @@ void segment_update(const Tensor& descs, const Tensor& tables, int64_t n_tables,
   opt.grad_scale = static_cast<float>(grad_scale);
   opt.weight_decay = static_cast<float>(weight_decay);
   opt.lr_ptr = reinterpret_cast<const float*>(lr_ptr);
+  opt.step_ptr = reinterpret_cast<const float*>(step_ptr);
   if (opt.kind == de::kOptEmit) TORCH_CHECK(emit_keys.has_value() && emit_rows.has_value());
   // occurrence-balanced path: immune to id skew (needs a zeroed scratch of >= n_items/32 rows)
   if (scratch.has_value() && vec4 && max_width <= 128 && opt.kind != de::kOptEmit) {
@@ -265,8 +321,8 @@ void segment_update(const Tensor& descs, const Tensor& tables, int64_t n_tables,
         batch, grad_batch, grad_stride, to_peers(grad_ptrs), sorted_keys.data_ptr<int64_t>(),
         reinterpret_cast<const uint32_t*>(sorted_items.data_ptr<int>()), n_items,
         seg_start.data_ptr<int64_t>(), n_unique.data_ptr<int64_t>(), opt,
-        scratch->data_ptr<float>(), static_cast<int>(sw), static_cast<int>(max_width), grad_bf16,
-        sm_count(), cur_stream());
+        scratch->data_ptr<float>(), static_cast<int>(sw), static_cast<int>(max_width),
+        static_cast<int>(act_dtype), sm_count(), cur_stream());
     TORCH_CHECK(ok, "balanced update launch failed");
     check_launch();
     return;
@@ -279,7 +335,7 @@ void segment_update(const Tensor& descs, const Tensor& tables, int64_t n_tables,
       seg_start.data_ptr<int64_t>(), n_unique.data_ptr<int64_t>(), sorted_keys.numel(), opt,
       emit_keys.has_value() ? emit_keys->data_ptr<int64_t>() : nullptr,
       emit_rows.has_value() ? emit_rows->data_ptr<float>() : nullptr, static_cast<int>(max_width),
-      grad_bf16, vec4, sm_count(), cur_stream());
+      static_cast<int>(act_dtype), vec4, sm_count(), cur_stream());
   check_launch();
 }
 
@@ -338,8 +394,8 @@ Tensor embedding_lookup_fwd(const Tensor& param, const Tensor& values,
   std::memset(&dst, 0, sizeof(dst));
   dst.p[0] = out.data_ptr();
   de::launch_lookup_fwd(reinterpret_cast<const de::InputDesc*>(dd.data_ptr()), 1, batch, batch,
-                        batch, width, src, dst, 0, values.scalar_type() == at::kLong, out_bf16,
-                        width % 4 == 0, sm_count(), cur_stream());
+                        batch, width, src, dst, 0, values.scalar_type() == at::kLong,
+                        out_bf16 ? 1 : 0, width % 4 == 0, sm_count(), cur_stream(), de::no_sync());
   check_launch();
   return out;
 }
@@ -362,15 +418,14 @@ void embedding_scatter_add(Tensor dst, const Tensor& values, const c10::optional
   std::memset(&src, 0, sizeof(src));
   std::memset(&gp, 0, sizeof(gp));
   gp.p[0] = grad.data_ptr();
-  const bool bf16 = grad.scalar_type() == at::kBFloat16;
-  TORCH_CHECK(bf16 || grad.scalar_type() == at::kFloat, "grad must be fp32 or bf16");
+  const int gdt = dtype_code(grad.scalar_type());
   const int64_t gstride = grad.stride(0);
   const bool vec4 = (width % 4 == 0) && (gstride % 4 == 0) &&
                     (reinterpret_cast<uintptr_t>(grad.data_ptr()) % 16 == 0);
   de::launch_scatter_add_bwd(reinterpret_cast<const de::InputDesc*>(dd.data_ptr()), 1, batch,
                              batch, batch, gstride, src, gp, 0, static_cast<float>(scale), nullptr,
-                             values.scalar_type() == at::kLong, bf16, vec4, sm_count(),
-                             cur_stream());
+                             values.scalar_type() == at::kLong, gdt, vec4, sm_count(),
+                             cur_stream(), false, de::no_sync());
   check_launch();
 }
 
@@ -398,14 +453,14 @@ std::tuple<Tensor, Tensor> embedding_lookup_grad(const Tensor& values,
                            n_items, num_rows, false);
   Tensor emit_keys = at::empty({n_items}, i64);
   Tensor emit_rows = at::empty({n_items, width}, f32);
-  const bool bf16 = grad.scalar_type() == at::kBFloat16;
+  const int gdt = dtype_code(grad.scalar_type());
   const int64_t gstride = grad.stride(0);
   const bool vec4 = (width % 4 == 0) && (gstride % 4 == 0) &&
                     (reinterpret_cast<uintptr_t>(grad.data_ptr()) % 16 == 0);
   std::vector<int64_t> gp = {reinterpret_cast<int64_t>(grad.data_ptr())};
   segment_update(dd, td, 1, batch, batch, gstride, gp, std::get<0>(sorted), std::get<1>(sorted),
                  std::get<2>(sorted), std::get<3>(sorted), de::kOptEmit, 0, 0, 0, 0, 1, 1, 1.0, 0, 0,
-                 emit_keys, emit_rows, width, bf16, vec4, c10::nullopt);
+                 emit_keys, emit_rows, width, gdt, vec4, c10::nullopt, 0);
   // sizing the IndexedSlices-style result needs the unique count on the host (compat path only)
   int64_t n_unique = std::get<3>(sorted).item<int64_t>();
   if (n_unique > 0) {
@@ -453,18 +508,18 @@ Tensor integer_lookup(Tensor table, Tensor count, Tensor next_index, const Tenso
 
 // ------------------------------------------------------------------ communication ops
 void barrier(at::IntArrayRef flag_ptrs, Tensor epoch, int64_t rank, int64_t world, int64_t channel,
-             int64_t timeout_cycles, Tensor error_flag) {
+             int64_t timeout_cycles, int64_t error_ptr) {
   c10::cuda::CUDAGuard guard(epoch.device());
   de::launch_barrier(to_peers(flag_ptrs), reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()),
                      static_cast<int>(rank), static_cast<int>(world), static_cast<int>(channel),
-                     static_cast<unsigned long long>(timeout_cycles), error_flag.data_ptr<int>(),
-                     cur_stream());
+                     static_cast<unsigned long long>(timeout_cycles),
+                     reinterpret_cast<int*>(error_ptr), cur_stream());
   check_launch();
 }
 
 void allreduce(at::IntArrayRef buf_ptrs, at::IntArrayRef flag_ptrs, Tensor epoch, int64_t rank,
                int64_t world, int64_t n_elems, double scale, bool bf16, int64_t channel,
-               int64_t timeout_cycles, Tensor error_flag, int64_t mc_ptr) {
+               int64_t timeout_cycles, int64_t error_ptr, int64_t mc_ptr, int64_t max_blocks) {
   c10::cuda::CUDAGuard guard(epoch.device());
   if (mc_ptr != 0) {
     de::launch_allreduce_multimem(reinterpret_cast<void*>(mc_ptr), to_peers(flag_ptrs),
@@ -472,15 +527,61 @@ void allreduce(at::IntArrayRef buf_ptrs, at::IntArrayRef flag_ptrs, Tensor epoch
                                   static_cast<int>(rank), static_cast<int>(world), n_elems,
                                   static_cast<float>(scale), bf16, static_cast<int>(channel),
                                   static_cast<unsigned long long>(timeout_cycles),
-                                  error_flag.data_ptr<int>(), sm_count(), cur_stream());
+                                  reinterpret_cast<int*>(error_ptr), sm_count(), cur_stream(),
+                         static_cast<int>(max_blocks));
   } else {
     de::launch_allreduce(to_peers(buf_ptrs), to_peers(flag_ptrs),
                          reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()),
                          static_cast<int>(rank), static_cast<int>(world), n_elems,
                          static_cast<float>(scale), bf16, static_cast<int>(channel),
                          static_cast<unsigned long long>(timeout_cycles),
-                         error_flag.data_ptr<int>(), sm_count(), cur_stream());
+                         reinterpret_cast<int*>(error_ptr), sm_count(), cur_stream(),
+                         static_cast<int>(max_blocks));
   }
+  check_launch();
+}
+
+// segs[j] = {dst_rank, src_elem_off, dst_elem_off, n_elems}: push id segments to their owners
+void push_segments(const Tensor& segs, const Tensor& src, at::IntArrayRef dst_ptrs,
+                   int64_t max_seg_elems, at::IntArrayRef sync) {
+  TORCH_CHECK(segs.is_cuda() && segs.scalar_type() == at::kLong && segs.is_contiguous() &&
+              segs.dim() == 2 && segs.size(1) == 4);
+  TORCH_CHECK(src.is_cuda() && src.is_contiguous() &&
+              (src.element_size() == 4 || src.element_size() == 8));
+  c10::cuda::CUDAGuard guard(src.device());
+  de::launch_push_segments(segs.data_ptr<int64_t>(), static_cast<int>(segs.size(0)),
+                           src.data_ptr(), to_peers(dst_ptrs),
+                           static_cast<int>(src.element_size()), max_seg_elems, sm_count(),
+                           cur_stream(), to_sync(sync));
+  check_launch();
+}
+
+// routes: raw bytes of a GradRoute array; src: local gradient rows [rows, *] (unit inner stride)
+void push_grad(const Tensor& routes, int64_t n_routes, const Tensor& src, int64_t dst_dtype,
+               double scale, at::IntArrayRef sync) {
+  TORCH_CHECK(routes.is_cuda() && routes.scalar_type() == at::kByte &&
+              routes.numel() >= n_routes * static_cast<int64_t>(sizeof(de::GradRoute)));
+  TORCH_CHECK(src.is_cuda() && src.dim() == 2 && src.stride(1) == 1);
+  c10::cuda::CUDAGuard guard(src.device());
+  de::launch_push_grad(reinterpret_cast<const de::GradRoute*>(routes.data_ptr()),
+                       static_cast<int>(n_routes), src.data_ptr(), src.stride(0),
+                       dtype_code(src.scalar_type()), static_cast<int>(dst_dtype), src.size(0),
+                       static_cast<float>(scale), sm_count(), cur_stream(), to_sync(sync));
+  check_launch();
+}
+
+// out[i, dst_col + c] = sum_s partial[s, i, src_col + c]; cols = int32 [n, 3] {src, dst, width}
+void rowslice_reduce(const Tensor& partial, int64_t out_ptr, int64_t out_stride,
+                     int64_t out_dtype, const Tensor& cols) {
+  TORCH_CHECK(partial.is_cuda() && partial.dim() == 3 && partial.scalar_type() == at::kFloat &&
+              partial.is_contiguous());
+  TORCH_CHECK(cols.is_cuda() && cols.scalar_type() == at::kInt && cols.is_contiguous() &&
+              cols.dim() == 2 && cols.size(1) == 3);
+  c10::cuda::CUDAGuard guard(partial.device());
+  de::launch_rowslice_reduce(partial.data_ptr<float>(), static_cast<int>(partial.size(0)),
+                             partial.size(1), partial.size(2), reinterpret_cast<void*>(out_ptr),
+                             out_stride, static_cast<int>(out_dtype), cols.data_ptr<int>(),
+                             static_cast<int>(cols.size(0)), cur_stream());
   check_launch();
 }
 
@@ -532,15 +633,13 @@ void select_copy(at::TensorList src0, at::TensorList src1, at::TensorList dst,
   check_launch();
 }
 
-void copy_cast_2d(const Tensor& src, int64_t dst_ptr, int64_t dst_stride, bool dst_bf16,
+void copy_cast_2d(const Tensor& src, int64_t dst_ptr, int64_t dst_stride, int64_t dst_dtype,
                   double scale) {
   TORCH_CHECK(src.is_cuda() && src.dim() == 2 && src.stride(1) == 1);
   c10::cuda::CUDAGuard guard(src.device());
-  const bool src_bf16 = src.scalar_type() == at::kBFloat16;
-  TORCH_CHECK(src_bf16 || src.scalar_type() == at::kFloat);
   de::launch_copy_cast_2d(src.data_ptr(), src.stride(0), reinterpret_cast<void*>(dst_ptr),
-                          dst_stride, src.size(0), src.size(1), src_bf16, dst_bf16,
-                          static_cast<float>(scale), cur_stream());
+                          dst_stride, src.size(0), src.size(1), dtype_code(src.scalar_type()),
+                          static_cast<int>(dst_dtype), static_cast<float>(scale), cur_stream());
   check_launch();
 }
 
@@ -551,7 +650,8 @@ void check_bf16_2d(const Tensor& t, const char* name) {
 }
 
 // z[s] = [strict lower triangle of F F^T | bottom | zero pad], F = [bottom ; emb_0 ; ...]
-void interact_fwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, Tensor z) {
+void interact_fwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, Tensor z,
+                  at::IntArrayRef sync) {
   check_bf16_2d(bottom, "bottom");
   check_bf16_2d(emb, "emb");
   check_bf16_2d(z, "z");
@@ -563,17 +663,21 @@ void interact_fwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, Tensor
   bool ok = de::launch_interact_fwd(bottom.data_ptr(), bottom.stride(0), emb.data_ptr(),
                                     emb.stride(0), static_cast<int>(n_emb), static_cast<int>(dim),
                                     z.data_ptr(), z.stride(0), static_cast<int>(z.size(1)),
-                                    bottom.size(0), sm_count(), cur_stream());
+                                    bottom.size(0), sm_count(), cur_stream(), to_sync(sync));
   TORCH_CHECK(ok, "unsupported interaction shape (n_emb <= 31, dim in {16,32,64,128})");
   check_launch();
 }
 
 void interact_bwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, const Tensor& dz,
-                  Tensor dbottom, int64_t demb_ptr, int64_t demb_stride, double emb_grad_scale) {
+                  Tensor dbottom, int64_t demb_ptr, int64_t demb_stride, double emb_grad_scale,
+                  const c10::optional<Tensor>& routes, int64_t n_routes, at::IntArrayRef sync) {
   check_bf16_2d(bottom, "bottom");
   check_bf16_2d(emb, "emb");
   check_bf16_2d(dz, "dz");
   check_bf16_2d(dbottom, "dbottom");
+  if (routes.has_value())
+    TORCH_CHECK(routes->is_cuda() && routes->scalar_type() == at::kByte &&
+                routes->numel() >= n_routes * static_cast<int64_t>(sizeof(de::GradRoute)));
   c10::cuda::CUDAGuard guard(bottom.device());
   const int64_t dim = bottom.size(1);
   bool ok = de::launch_interact_bwd(bottom.data_ptr(), bottom.stride(0), emb.data_ptr(),
@@ -581,8 +685,13 @@ void interact_bwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, const 
                                     dz.data_ptr(), dz.stride(0), dbottom.data_ptr(),
                                     dbottom.stride(0), reinterpret_cast<void*>(demb_ptr),
                                     demb_stride, static_cast<float>(emb_grad_scale),
-                                    bottom.size(0), sm_count(), cur_stream());
-  TORCH_CHECK(ok, "unsupported interaction shape (n_emb <= 31, dim in {32,64,128})");
+                                    bottom.size(0), sm_count(), cur_stream(),
+                                    routes.has_value()
+                                        ? reinterpret_cast<const de::GradRoute*>(routes->data_ptr())
+                                        : nullptr,
+                                    static_cast<int>(n_routes), to_sync(sync));
+  TORCH_CHECK(ok, "unsupported interaction shape (n_emb <= 31, dim in {32,64,128}; routed / "
+                  "signalling launches need dim in {64,128} and 16-byte aligned rows)");
   check_launch();
 }
 
@@ -734,24 +843,20 @@ int64_t host_device_pointer(const Tensor& host) {
 TORCH_LIBRARY(de_b200, m) {
   m.def("struct_sizes() -> int[]", &struct_sizes);
   m.def(
+      "sync_ctx_create(int[] flag_ptrs, Tensor state, int rank, int world, int timeout_cycles, "
+      "int error_ptr) -> int",
+      &sync_ctx_create);
+  m.def("sync_only(int[] sync) -> ()", &sync_only);
+  m.def(
       "lookup_fwd(Tensor descs, int n_inputs, int batch, int src_batch, int dst_batch, "
-      "int dst_stride, int[] src_ptrs, int[] dst_ptrs, int rot, bool ids64, bool out_bf16, "
-      "bool vec4) -> ()",
+      "int dst_stride, int[] src_ptrs, int[] dst_ptrs, int rot, bool ids64, int act_dtype, "
+      "bool vec4, int[] sync) -> ()",
       &lookup_fwd);
   m.def(
       "scatter_add_bwd(Tensor descs, int n_inputs, int batch, int src_batch, int grad_batch, "
       "int grad_stride, int[] src_ptrs, int[] grad_ptrs, int rot, float scale, int scale_ptr, bool ids64, "
-      "bool grad_bf16, bool vec4, bool vec8) -> ()",
+      "int act_dtype, bool vec4, bool vec8, int[] sync) -> ()",
       &scatter_add_bwd);
-  m.def(
-      "lookup_fwd_bulk(Tensor descs, int n_inputs, int batch, int src_batch, int dst_batch, "
-      "int dst_stride, int[] src_ptrs, int[] dst_ptrs, int rot, bool ids64, bool out_bf16) -> ()",
-      &lookup_fwd_bulk);
-  m.def(
-      "tiny_scatter_add_bwd(Tensor descs, int n_inputs, int batch, int src_batch, int grad_batch, "
-      "int grad_stride, int[] src_ptrs, int[] grad_ptrs, float scale, int scale_ptr, bool ids64, "
-      "bool grad_bf16, int max_rows, int max_width) -> ()",
-      &tiny_scatter_add_bwd);
   m.def(
       "sort_items(Tensor descs, Tensor tables, int n_tables, int n_inputs, int batch, "
       "int src_batch, int[] src_ptrs, bool ids64, int n_items, int total_rows, "
@@ -766,8 +871,8 @@ TORCH_LIBRARY(de_b200, m) {
       "int grad_stride, int[] grad_ptrs, Tensor sorted_keys, Tensor sorted_items, "
       "Tensor seg_start, Tensor n_unique, int opt_kind, float lr, float eps, float beta1, "
       "float beta2, float bias1, float bias2, float grad_scale, float weight_decay, int lr_ptr, "
-      "Tensor? emit_keys, Tensor? emit_rows, int max_width, bool grad_bf16, bool vec4, "
-      "Tensor? scratch) -> ()",
+      "Tensor? emit_keys, Tensor? emit_rows, int max_width, int act_dtype, bool vec4, "
+      "Tensor? scratch, int step_ptr) -> ()",
       &segment_update);
   m.def(
       "embedding_lookup_fwd(Tensor param, Tensor values, Tensor? offsets, int hotness, int batch, "
@@ -789,27 +894,40 @@ TORCH_LIBRARY(de_b200, m) {
       &integer_lookup);
   m.def(
       "barrier(int[] flag_ptrs, Tensor(a!) epoch, int rank, int world, int channel, "
-      "int timeout_cycles, Tensor(b!) error_flag) -> ()",
+      "int timeout_cycles, int error_ptr) -> ()",
       &barrier);
   m.def(
       "allreduce(int[] buf_ptrs, int[] flag_ptrs, Tensor(a!) epoch, int rank, int world, "
       "int n_elems, float scale, bool bf16, int channel, int timeout_cycles, "
-      "Tensor(b!) error_flag, int mc_ptr) -> ()",
+      "int error_ptr, int mc_ptr, int max_blocks) -> ()",
       &allreduce);
   m.def("gather_segments(Tensor segs, int[] src_ptrs, Tensor(a!) dst, int max_seg_elems) -> ()",
         &gather_segments);
+  m.def(
+      "push_segments(Tensor segs, Tensor src, int[] dst_ptrs, int max_seg_elems, int[] sync) -> ()",
+      &push_segments);
+  m.def(
+      "push_grad(Tensor routes, int n_routes, Tensor src, int dst_dtype, float scale, int[] sync) "
+      "-> ()",
+      &push_grad);
+  m.def(
+      "rowslice_reduce(Tensor partial, int out_ptr, int out_stride, int out_dtype, Tensor cols) "
+      "-> ()",
+      &rowslice_reduce);
   m.def(
       "gather_ragged(Tensor segs, int[] val_ptrs, int[] split_ptrs, Tensor(a!) dst_vals, "
       "Tensor(b!) goff, int b, int max_cap) -> ()",
       &gather_ragged);
   m.def("select_copy(Tensor[] src0, Tensor[] src1, Tensor(a!)[] dst, Tensor slot_flag) -> ()",
         &select_copy);
-  m.def("copy_cast_2d(Tensor src, int dst_ptr, int dst_stride, bool dst_bf16, float scale) -> ()",
+  m.def("copy_cast_2d(Tensor src, int dst_ptr, int dst_stride, int dst_dtype, float scale) -> ()",
         &copy_cast_2d);
-  m.def("interact_fwd(Tensor bottom, Tensor emb, int n_emb, Tensor(a!) z) -> ()", &interact_fwd);
+  m.def("interact_fwd(Tensor bottom, Tensor emb, int n_emb, Tensor(a!) z, int[] sync) -> ()",
+        &interact_fwd);
   m.def(
       "interact_bwd(Tensor bottom, Tensor emb, int n_emb, Tensor dz, Tensor(a!) dbottom, "
-      "int demb_ptr, int demb_stride, float emb_grad_scale) -> ()",
+      "int demb_ptr, int demb_stride, float emb_grad_scale, Tensor? routes, int n_routes, "
+      "int[] sync) -> ()",
       &interact_bwd);
   m.def("relu_bwd_bias(Tensor(a!) dy, Tensor y, Tensor(b!) db) -> ()", &relu_bwd_bias);
   m.def(

@@ -5,6 +5,8 @@
 // (multimem.ld_reduce / multimem.st -> in-switch reduction).
 //
 // Replaces Horovod's allreduce / barrier use (reference dist_model_parallel.py:1260, 985).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace de {
@@ -21,9 +23,8 @@ __global__ void barrier_kernel(const __grid_constant__ PeerPtrs flags, uint32_t*
   if (t < world) {
     __threadfence_system();
     st_release_sys(flag_slot(flags.p[t], channel, rank), epoch);
-    if (!wait_flag_ge(flag_slot(flags.p[rank], channel, t), epoch, timeout_cycles)) {
-      if (error_flag) atomicExch(error_flag, 1 + t);
-    }
+    if (!wait_flag_ge(flag_slot(flags.p[rank], channel, t), epoch, timeout_cycles))
+      peer_timeout_trap(error_flag, t);  // never continue (or advance the epoch) past a lost peer
   }
   __syncthreads();
   if (t == 0) *epoch_p = epoch;
@@ -40,9 +41,8 @@ __device__ __forceinline__ void grid_peer_barrier_enter(const PeerPtrs& flags, u
       __threadfence_system();
       st_release_sys(flag_slot(flags.p[t], channel, rank), epoch);
     }
-    if (!wait_flag_ge(flag_slot(flags.p[rank], channel, t), epoch, timeout_cycles)) {
-      if (error_flag) atomicExch(error_flag, 1 + t);
-    }
+    if (!wait_flag_ge(flag_slot(flags.p[rank], channel, t), epoch, timeout_cycles))
+      peer_timeout_trap(error_flag, t);  // never continue (or advance the epoch) past a lost peer
   }
   __syncthreads();
 }
@@ -67,9 +67,8 @@ __device__ __forceinline__ void grid_peer_barrier_exit(const PeerPtrs& flags, ui
   if (t < world) {
     __threadfence_system();
     st_release_sys(flag_slot(flags.p[t], channel, rank), epoch);
-    if (!wait_flag_ge(flag_slot(flags.p[rank], channel, t), epoch, timeout_cycles)) {
-      if (error_flag) atomicExch(error_flag, 1 + t);
-    }
+    if (!wait_flag_ge(flag_slot(flags.p[rank], channel, t), epoch, timeout_cycles))
+      peer_timeout_trap(error_flag, t);  // never continue (or advance the epoch) past a lost peer
   }
   __syncthreads();
   if (t == 0) {
@@ -206,6 +205,133 @@ allreduce_multimem_kernel(void* mc_ptr, const __grid_constant__ PeerPtrs flags, 
                          timeout_cycles, error_flag);
 }
 
+// ----------------------------------------------------------------------------- signalling only
+__global__ void sync_only_kernel(const __grid_constant__ SyncArgs sync) {
+  sync_head(sync);
+  sync_tail(sync);
+}
+
+// ----------------------------------------------------------------------------- index push
+// Push-style all-to-all of index segments: segment j copies n elements of the local staging
+// buffer into the id buffer of the rank that owns the feature (fire-and-forget NVLink stores;
+// the reference's 'inp_dp_to_mp' hvd.alltoall, dist_model_parallel.py:211).  The head waits
+// until every owner has consumed the ids of the previous step (wait_abs on the "consumed"
+// channel), the tail tells the owners that their ids are complete.
+template <typename T>
+__global__ void __launch_bounds__(256)
+push_segments_kernel(const int64_t* __restrict__ segs, int n_seg, const T* __restrict__ src,
+                     const __grid_constant__ PeerPtrs dst, int blocks_per_seg,
+                     const __grid_constant__ SyncArgs sync) {
+  sync_head(sync);
+  const int j = blockIdx.x / blocks_per_seg;
+  const int bj = blockIdx.x - j * blocks_per_seg;
+  if (j < n_seg) {
+    const int64_t* sg = segs + 4 * static_cast<int64_t>(j);
+    const T* sp = src + sg[1];
+    T* dp = reinterpret_cast<T*>(dst.p[sg[0]]) + sg[2];
+    const int64_t n = sg[3];
+    constexpr int kPer16 = 16 / sizeof(T);
+    const int64_t stride = static_cast<int64_t>(blocks_per_seg) * blockDim.x;
+    const int64_t t0 = static_cast<int64_t>(bj) * blockDim.x + threadIdx.x;
+    if (((reinterpret_cast<uintptr_t>(sp) | reinterpret_cast<uintptr_t>(dp)) & 15) == 0) {
+      const int64_t n16 = n / kPer16;
+      for (int64_t i = t0; i < n16; i += stride)
+        reinterpret_cast<uint4*>(dp)[i] = reinterpret_cast<const uint4*>(sp)[i];
+      for (int64_t i = n16 * kPer16 + t0; i < n; i += stride) dp[i] = sp[i];
+    } else {
+      for (int64_t i = t0; i < n; i += stride) dp[i] = sp[i];
+    }
+  }
+  sync_tail(sync);
+}
+
+// ----------------------------------------------------------------------------- gradient push
+// The gradient all-to-all (Horovod's alltoall gradient in the reference) as a push: block row
+// tiles x route pieces; every piece of a local gradient row is cast to the wire dtype and
+// stored into the receive buffer of the rank that owns the table (slice).  16-byte stores when
+// the piece allows it.
+template <typename S, typename D>
+__global__ void __launch_bounds__(256)
+push_grad_kernel(const GradRoute* __restrict__ routes, int n_routes, const S* __restrict__ src,
+                 int64_t src_stride, int64_t rows, float scale,
+                 const __grid_constant__ SyncArgs sync) {
+  sync_head(sync);
+  constexpr int kRowsPerTile = 8;
+  const int64_t n_row_tiles = (rows + kRowsPerTile - 1) / kRowsPerTile;
+  const int64_t total = n_row_tiles * n_routes;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int r = static_cast<int>(t % n_routes);
+    const int64_t row0 = (t / n_routes) * kRowsPerTile;
+    const GradRoute R = routes[r];
+    D* dst = reinterpret_cast<D*>(R.dst);
+    const int64_t left = rows - row0;
+    const int nr = left < kRowsPerTile ? static_cast<int>(left) : kRowsPerTile;
+    constexpr int kVec = 16 / sizeof(D);  // elements per 16-byte store
+    const bool vec = (R.width % kVec == 0) && (R.dst_col % kVec == 0) &&
+                     (R.dst_stride % kVec == 0) && (R.src_col % 4 == 0) && (src_stride % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (vec) {
+      const int chunks = R.width / kVec;
+      for (int c = threadIdx.x; c < nr * chunks; c += blockDim.x) {
+        const int rr = c / chunks, ch = c - rr * chunks;
+        const S* sp = src + (row0 + rr) * src_stride + R.src_col + ch * kVec;
+        float v[kVec];
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) v[k] = to_f32<S>(sp[k]) * scale;
+        D* dp = dst + (row0 + rr) * R.dst_stride + R.dst_col + ch * kVec;
+        if constexpr (sizeof(D) == 4) {
+          *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          uint4 o;
+          o.x = pack2<D>(v[0], v[1]);
+          o.y = pack2<D>(v[2], v[3]);
+          o.z = pack2<D>(v[4], v[5]);
+          o.w = pack2<D>(v[6], v[7]);
+          *reinterpret_cast<uint4*>(dp) = o;
+        }
+      }
+    } else {
+      for (int c = threadIdx.x; c < nr * R.width; c += blockDim.x) {
+        const int rr = c / R.width, cc = c - rr * R.width;
+        dst[(row0 + rr) * R.dst_stride + R.dst_col + cc] =
+            from_f32<D>(to_f32<S>(src[(row0 + rr) * src_stride + R.src_col + cc]) * scale);
+      }
+    }
+  }
+  sync_tail(sync);
+}
+
+// ----------------------------------------------------------------------------- row-slice sum
+// Multi-hot row-sliced inputs: every rank pooled the ids it owns and stored its partial result
+// in slot `rank` of the requester; the requester sums the W slots into its output row (the
+// reference's reduce-scatter, dist_model_parallel.py:291-298, without the W-fold redundancy in
+// the output direction).
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+rowslice_reduce_kernel(const float* __restrict__ partial, int world, int64_t rows,
+                       int64_t part_stride, OutT* __restrict__ out, int64_t out_stride,
+                       const int32_t* __restrict__ cols, int n_cols, int total_width) {
+  const int64_t n = rows * total_width;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    const int64_t r = i / total_width;
+    int c = static_cast<int>(i - r * total_width);
+    // find the column group (few groups: linear scan)
+    int j = 0, base = 0;
+    while (j < n_cols - 1 && c >= base + cols[3 * j + 2]) {
+      base += cols[3 * j + 2];
+      ++j;
+    }
+    c -= base;
+    float acc = 0.f;
+    for (int s = 0; s < world; ++s)
+      acc += partial[(static_cast<int64_t>(s) * rows + r) * part_stride + cols[3 * j] + c];
+    out[r * out_stride + cols[3 * j + 1] + c] = from_f32<OutT>(acc);
+  }
+}
+
 // Pull-style all-to-all of index segments: segment j copies n elements from peer src_rank's
 // staging buffer into the local model-parallel id buffer (the reference's 'inp_dp_to_mp'
 // hvd.alltoall, dist_model_parallel.py:211, as direct NVLink reads).
@@ -288,12 +414,7 @@ __global__ void copy_cast_2d_kernel(const S* __restrict__ src, int64_t src_strid
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += stride) {
     const int64_t r = i / cols, c = i - r * cols;
-    float v;
-    if constexpr (sizeof(S) == 4) v = src[r * src_stride + c];
-    else v = __bfloat162float(src[r * src_stride + c]);
-    v *= scale;
-    if constexpr (sizeof(D) == 4) dst[r * dst_stride + c] = v;
-    else dst[r * dst_stride + c] = __float2bfloat16_rn(v);
+    dst[r * dst_stride + c] = from_f32<D>(to_f32<S>(src[r * src_stride + c]) * scale);
   }
 }
 
@@ -309,12 +430,16 @@ void launch_barrier(const PeerPtrs& flags, uint32_t* epoch, int rank, int world,
 void launch_allreduce(const PeerPtrs& bufs, const PeerPtrs& flags, uint32_t* epoch, int rank,
                       int world, int64_t n_elems, float scale, bool bf16, int channel,
                       unsigned long long timeout_cycles, int* error_flag, int sm_count,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int max_blocks) {
   const int64_t per16 = bf16 ? 8 : 4;
   const int64_t n_vec16 = (n_elems + per16 - 1) / per16;  // buffers are padded to 16 bytes
   const int threads = 512;
   int64_t blocks = ((n_vec16 + world - 1) / world + threads - 1) / threads;
-  if (blocks > sm_count) blocks = sm_count;  // must be co-resident: blocks spin on flags
+  if (blocks > sm_count) blocks = sm_count;  // at most one wave: blocks spin on flags
+  // an all-reduce that overlaps other kernels must leave most SMs to them: its blocks spin on
+  // peer flags, and a spinning grid that fills the machine can starve the very kernels the
+  // peers are waiting for
+  if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   if (bf16)
     allreduce_p2p_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
@@ -329,12 +454,13 @@ void launch_allreduce(const PeerPtrs& bufs, const PeerPtrs& flags, uint32_t* epo
 void launch_allreduce_multimem(void* mc_ptr, const PeerPtrs& flags, uint32_t* epoch, int rank,
                                int world, int64_t n_elems, float scale, bool bf16, int channel,
                                unsigned long long timeout_cycles, int* error_flag, int sm_count,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, int max_blocks) {
   const int64_t per16 = bf16 ? 8 : 4;
   const int64_t n_vec16 = (n_elems + per16 - 1) / per16;
   const int threads = 512;
   int64_t blocks = ((n_vec16 + world - 1) / world + threads - 1) / threads;
   if (blocks > sm_count) blocks = sm_count;
+  if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   if (bf16)
     allreduce_multimem_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
@@ -411,12 +537,12 @@ __global__ void copy_2d_vec16_kernel(const uint4* __restrict__ src, int64_t src_
 }
 
 void launch_copy_cast_2d(const void* src, int64_t src_stride, void* dst, int64_t dst_stride,
-                         int64_t rows, int64_t cols, bool src_bf16, bool dst_bf16, float scale,
+                         int64_t rows, int64_t cols, int src_dtype, int dst_dtype, float scale,
                          cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return;
   {
-    const int64_t per16 = src_bf16 ? 8 : 4;
-    if (src_bf16 == dst_bf16 && scale == 1.0f && cols % per16 == 0 && src_stride % per16 == 0 &&
+    const int64_t per16 = src_dtype == 0 ? 4 : 8;
+    if (src_dtype == dst_dtype && scale == 1.0f && cols % per16 == 0 && src_stride % per16 == 0 &&
         dst_stride % per16 == 0 &&
         ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
       const int64_t n = rows * (cols / per16);
@@ -435,14 +561,96 @@ void launch_copy_cast_2d(const void* src, int64_t src_stride, void* dst, int64_t
   copy_cast_2d_kernel<S, D><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(              \
       reinterpret_cast<const S*>(src), src_stride, reinterpret_cast<D*>(dst), dst_stride, rows,  \
       cols, scale)
-  if (src_bf16) {
-    if (dst_bf16) DE_CC(__nv_bfloat16, __nv_bfloat16);
-    else DE_CC(__nv_bfloat16, float);
-  } else {
-    if (dst_bf16) DE_CC(float, __nv_bfloat16);
-    else DE_CC(float, float);
-  }
+#define DE_CC_D(S)                                                                               \
+  do {                                                                                           \
+    if (dst_dtype == 1) DE_CC(S, __nv_bfloat16);                                                 \
+    else if (dst_dtype == 2) DE_CC(S, __half);                                                   \
+    else DE_CC(S, float);                                                                        \
+  } while (0)
+  if (src_dtype == 1) DE_CC_D(__nv_bfloat16);
+  else if (src_dtype == 2) DE_CC_D(__half);
+  else DE_CC_D(float);
+#undef DE_CC_D
 #undef DE_CC
+}
+
+void launch_sync_only(const SyncArgs& sync, cudaStream_t stream) {
+  if (sync.state == nullptr || (sync.wait_ch < 0 && sync.wait_abs_ch < 0 && sync.signal_ch < 0))
+    return;
+  sync_only_kernel<<<1, 32, 0, stream>>>(sync);
+}
+
+void launch_push_segments(const int64_t* segs, int n_seg, const void* src, const PeerPtrs& dst,
+                          int elem_bytes, int64_t max_seg_elems, int sm_count,
+                          cudaStream_t stream, const SyncArgs& sync) {
+  if (n_seg <= 0 || max_seg_elems <= 0) {
+    launch_sync_only(sync, stream);
+    return;
+  }
+  // 16-byte copies, 4 per thread: enough blocks per segment to cover the longest one, but never
+  // more than one wave (every block spins in sync_head until the peers are ready)
+  const int64_t per_block = 256 * 4 * (16 / elem_bytes);
+  int64_t bps = (max_seg_elems + per_block - 1) / per_block;
+  const int64_t cap = std::max<int64_t>(1, (static_cast<int64_t>(sm_count) * 4) / n_seg);
+  if (bps > cap) bps = cap;
+  if (bps < 1) bps = 1;
+  const unsigned grid = static_cast<unsigned>(bps * n_seg);
+  if (elem_bytes == 8)
+    push_segments_kernel<int64_t><<<grid, 256, 0, stream>>>(
+        segs, n_seg, reinterpret_cast<const int64_t*>(src), dst, static_cast<int>(bps), sync);
+  else
+    push_segments_kernel<int32_t><<<grid, 256, 0, stream>>>(
+        segs, n_seg, reinterpret_cast<const int32_t*>(src), dst, static_cast<int>(bps), sync);
+}
+
+void launch_push_grad(const GradRoute* routes, int n_routes, const void* src, int64_t src_stride,
+                      int src_dtype, int dst_dtype, int64_t rows, float scale, int sm_count,
+                      cudaStream_t stream, const SyncArgs& sync) {
+  if (n_routes <= 0 || rows <= 0) {
+    launch_sync_only(sync, stream);
+    return;
+  }
+  const int64_t total = ((rows + 7) / 8) * n_routes;
+  int64_t blocks = total;
+  if (blocks > static_cast<int64_t>(sm_count) * 8) blocks = static_cast<int64_t>(sm_count) * 8;
+#define DE_PG(S, D)                                                                               \
+  push_grad_kernel<S, D><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(                      \
+      routes, n_routes, reinterpret_cast<const S*>(src), src_stride, rows, scale, sync)
+#define DE_PG_D(S)                                                                                \
+  do {                                                                                            \
+    if (dst_dtype == 1) DE_PG(S, __nv_bfloat16);                                                  \
+    else if (dst_dtype == 2) DE_PG(S, __half);                                                    \
+    else DE_PG(S, float);                                                                         \
+  } while (0)
+  if (src_dtype == 1) DE_PG_D(__nv_bfloat16);
+  else if (src_dtype == 2) DE_PG_D(__half);
+  else DE_PG_D(float);
+#undef DE_PG_D
+#undef DE_PG
+}
+
+void launch_rowslice_reduce(const float* partial, int world, int64_t rows, int64_t part_stride,
+                            void* out, int64_t out_stride, int out_dtype, const int32_t* cols,
+                            int n_cols, cudaStream_t stream) {
+  if (rows <= 0 || n_cols <= 0) return;
+  // total width is the sum of the group widths: computed on the host by the caller's layout
+  // (cols lives on the device), so it is passed through part_stride == total width
+  const int total_width = static_cast<int>(part_stride);
+  const int64_t n = rows * total_width;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (out_dtype == 1)
+    rowslice_reduce_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        partial, world, rows, part_stride, reinterpret_cast<__nv_bfloat16*>(out), out_stride, cols,
+        n_cols, total_width);
+  else if (out_dtype == 2)
+    rowslice_reduce_kernel<__half><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        partial, world, rows, part_stride, reinterpret_cast<__half*>(out), out_stride, cols,
+        n_cols, total_width);
+  else
+    rowslice_reduce_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        partial, world, rows, part_stride, reinterpret_cast<float*>(out), out_stride, cols, n_cols,
+        total_width);
 }
 
 }  // namespace de

@@ -31,6 +31,48 @@ struct PeerPtrs {
   void* p[kMaxPeers];
 };
 
+// Cross-GPU producer/consumer signalling folded into the data kernels (no separate barrier
+// launches): a kernel may *wait* at its head for the peers' signals on one channel and *signal*
+// all peers from its tail once every block has finished.  Flags are per (channel, writer)
+// epoch words in the peer-mapped signal pad; the epochs a rank expects / publishes live in
+// device memory (`state`), so a captured CUDA graph replays without host patching.
+//   state[0..15]   wait epochs   (signals consumed per channel)
+//   state[16..31]  signal epochs (signals published per channel)
+//   state[32..63]  block counters (one per call site: `counter_slot`)
+constexpr int kSyncChannels = 16;
+constexpr int kSyncStateWords = 64;
+struct SyncArgs {
+  PeerPtrs flags;               // signal pads of all ranks (peer mapped)
+  uint32_t* state;              // this rank's epoch / counter words (nullptr = no signalling)
+  int* error_flag;              // host-mapped watchdog word (may be nullptr)
+  unsigned long long timeout;   // cycles before a wait gives up and traps (0 = wait forever)
+  int32_t rank, world;
+  int32_t wait_ch;              // >= 0: wait until every peer's flag >= wait epoch + 1
+  int32_t wait_abs_ch;          // >= 0: wait until every peer's flag >= this rank's *signal*
+                                //       epoch of that channel (peers have caught up with me)
+  int32_t signal_ch;            // >= 0: publish signal epoch + 1 to every peer at the tail
+  int32_t counter_slot;         // block counter used by this launch (unique per call site)
+};
+inline SyncArgs no_sync() {
+  SyncArgs s{};
+  s.state = nullptr;
+  s.wait_ch = s.wait_abs_ch = s.signal_ch = -1;
+  return s;
+}
+
+// One contiguous piece of a requester-side gradient row and where it goes on its owner:
+// columns [src_col, src_col + width) of local sample i land at
+// dst + i * dst_stride + dst_col (dst already points at this requester's row block of the
+// owner's receive buffer; peer mapped).
+struct alignas(16) GradRoute {
+  void* dst;
+  int64_t dst_stride;  // elements
+  int32_t src_col;
+  int32_t width;
+  int32_t dst_col;
+  int32_t pad;
+};
+
 enum OptimizerKind : int32_t { kOptSGD = 0, kOptAdagrad = 1, kOptRowwiseAdagrad = 2, kOptAdam = 3, kOptEmit = 4 };
 
 // One entry per (fused) local table, used by the sorted/deduplicated update path.
@@ -53,15 +95,18 @@ struct OptimizerArgs {
   float grad_scale;    // applied to the summed gradient (1/world for the global-mean contract)
   float weight_decay;
   const float* lr_ptr;  // optional device-resident learning rate (overrides lr; graph replay safe)
+  const float* step_ptr;  // optional device-resident Adam step count t (bias1/bias2 are then
+                          // recomputed as 1 - beta^t on the device; graph replay safe)
 };
 
 // ---- pooled lookup forward (+ optional fused push to peer output buffers) ------------------
 // ids come from src.p[g / src_batch] (peer mapped) or desc.ids; pooled rows are stored to
 // dst.p[g / dst_batch] + (g % dst_batch) * dst_stride + dst_col.
+// act_dtype: 0 = fp32, 1 = bf16, 2 = fp16 (dtype of the activations / gradients on the wire)
 void launch_lookup_fwd(const InputDesc* descs, int n_inputs, int64_t batch, int64_t src_batch,
                        int64_t dst_batch, int64_t dst_stride, const PeerPtrs& src,
-                       const PeerPtrs& dst, int rot, bool ids64, bool out_bf16, bool vec4,
-                       int sm_count, cudaStream_t stream);
+                       const PeerPtrs& dst, int rot, bool ids64, int act_dtype, bool vec4,
+                       int sm_count, cudaStream_t stream, const SyncArgs& sync);
 
 // ---- backward: atomic scatter-add of (scaled) gradient rows into the table (SGD fast path,
 // also used to build dense gradients of replicated tables). Gradient rows are pulled from
@@ -69,21 +114,8 @@ void launch_lookup_fwd(const InputDesc* descs, int n_inputs, int64_t batch, int6
 void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch, int64_t src_batch,
                             int64_t grad_batch, int64_t grad_stride, const PeerPtrs& src,
                             const PeerPtrs& grad, int rot, float scale, const float* scale_ptr,
-                            bool ids64, bool grad_bf16, bool vec4, int sm_count,
-                            cudaStream_t stream, bool vec8 = false);
-
-// one-hot forward through TMA bulk row copies (experimental, see lookup_kernels.cu)
-bool launch_lookup_fwd_bulk(const InputDesc* descs, int n_inputs, int64_t batch,
-                            int64_t src_batch, int64_t dst_batch, int64_t dst_stride,
-                            const PeerPtrs& src, const PeerPtrs& dst, int rot, bool ids64,
-                            bool out_bf16, int sm_count, cudaStream_t stream);
-
-// tiny one-hot tables: shared-memory pre-reduction (see lookup_kernels.cu)
-bool launch_tiny_scatter_add(const InputDesc* descs, int n_inputs, int64_t batch,
-                             int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
-                             const PeerPtrs& src, const PeerPtrs& grad, float scale,
-                             const float* scale_ptr, bool ids64, bool grad_bf16, int max_rows,
-                             int max_width, cudaStream_t stream);
+                            bool ids64, int act_dtype, bool vec4, int sm_count,
+                            cudaStream_t stream, bool vec8, const SyncArgs& sync);
 
 // ---- backward: sorted / deduplicated path -----------------------------------------------
 void launch_build_keys(const InputDesc* descs, const TableDesc* tables, int n_tables, int n_inputs,
@@ -109,7 +141,7 @@ void launch_segment_update(const InputDesc* descs, const TableDesc* tables, int 
                            const PeerPtrs& grad, const int64_t* sorted_keys,
                            const uint32_t* sorted_items, const int64_t* seg_start,
                            const int64_t* n_unique, int64_t n_items, const OptimizerArgs& opt,
-                           int64_t* emit_keys, float* emit_rows, int max_width, bool grad_bf16,
+                           int64_t* emit_keys, float* emit_rows, int max_width, int act_dtype,
                            bool vec4, int sm_count, cudaStream_t stream);
 
 bool launch_balanced_update(const InputDesc* descs, const TableDesc* tables, int n_tables,
@@ -118,7 +150,7 @@ bool launch_balanced_update(const InputDesc* descs, const TableDesc* tables, int
                             const uint32_t* sorted_items, int64_t n_items,
                             const int64_t* seg_start, const int64_t* n_unique,
                             const OptimizerArgs& opt, float* scratch, int scratch_width,
-                            int max_width, bool grad_bf16, int sm_count, cudaStream_t stream);
+                            int max_width, int act_dtype, int sm_count, cudaStream_t stream);
 
 // ---- misc ---------------------------------------------------------------------------------
 void launch_row_to_split(const int64_t* coo_indices, int64_t nnz, int64_t num_rows,
@@ -137,12 +169,31 @@ void launch_barrier(const PeerPtrs& flags, uint32_t* epoch, int rank, int world,
 void launch_allreduce(const PeerPtrs& bufs, const PeerPtrs& flags, uint32_t* epoch, int rank,
                       int world, int64_t n_elems, float scale, bool bf16, int channel,
                       unsigned long long timeout_cycles, int* error_flag, int sm_count,
-                      cudaStream_t stream);
+                      cudaStream_t stream, int max_blocks = 0);
 // Multimem (NVLS) variant: mc_ptr is the multicast mapping of the same symmetric buffer.
 void launch_allreduce_multimem(void* mc_ptr, const PeerPtrs& flags, uint32_t* epoch, int rank,
                                int world, int64_t n_elems, float scale, bool bf16, int channel,
                                unsigned long long timeout_cycles, int* error_flag, int sm_count,
-                               cudaStream_t stream);
+                               cudaStream_t stream, int max_blocks = 0);
+// Standalone signalling kernel (one block): the wait / signal parts of `sync` without any data.
+void launch_sync_only(const SyncArgs& sync, cudaStream_t stream);
+// Segmented P2P *push* of index segments into the owners' id buffers (the reference's
+// 'inp_dp_to_mp' all-to-all as fire-and-forget NVLink stores):
+// segs[j] = {dst_rank, src_elem_off, dst_elem_off, n_elems}
+void launch_push_segments(const int64_t* segs, int n_seg, const void* src, const PeerPtrs& dst,
+                          int elem_bytes, int64_t max_seg_elems, int sm_count,
+                          cudaStream_t stream, const SyncArgs& sync);
+// Gradient all-to-all as a push: every route piece of the local gradient rows [rows, *] is cast
+// to the wire dtype and stored into its owner's receive buffer.  src_dtype / dst_dtype: 0 fp32,
+// 1 bf16, 2 fp16.
+void launch_push_grad(const GradRoute* routes, int n_routes, const void* src, int64_t src_stride,
+                      int src_dtype, int dst_dtype, int64_t rows, float scale, int sm_count,
+                      cudaStream_t stream, const SyncArgs& sync);
+// out[i, dst_col + c] = sum_s partial[s][i, src_col + c]: requester-side sum of the W partial
+// pools of multi-hot row-sliced inputs.  cols[j] = {src_col, dst_col, width}
+void launch_rowslice_reduce(const float* partial, int world, int64_t rows, int64_t part_stride,
+                            void* out, int64_t out_stride, int out_dtype, const int32_t* cols,
+                            int n_cols, cudaStream_t stream);
 // Segmented P2P pull: segs[j] = {src_rank, src_elem_off, dst_elem_off, n_elems}
 void launch_gather_segments(const int64_t* segs, int n_seg, const PeerPtrs& src, void* dst,
                             int elem_bytes, int64_t max_seg_elems, cudaStream_t stream);
@@ -156,18 +207,23 @@ void launch_select_copy(const void* const* src0, const void* const* src1, void* 
                         cudaStream_t stream);
 // Copy/cast a strided 2-D block into a (symmetric) buffer: dst[r, c] = cast(src[r, c])
 void launch_copy_cast_2d(const void* src, int64_t src_stride, void* dst, int64_t dst_stride,
-                         int64_t rows, int64_t cols, bool src_bf16, bool dst_bf16, float scale,
+                         int64_t rows, int64_t cols, int src_dtype, int dst_dtype, float scale,
                          cudaStream_t stream);
 
 // ---- dense-side kernels (DLRM interaction, fused elementwise + loss + optimizer) ------------
 bool launch_interact_fwd(const void* bottom, int64_t bottom_stride, const void* emb,
                          int64_t emb_stride, int n_emb, int dim, void* z, int64_t z_stride,
-                         int z_width, int64_t batch, int sm_count, cudaStream_t stream);
+                         int z_width, int64_t batch, int sm_count, cudaStream_t stream,
+                         const SyncArgs& sync);
+// The embedding gradient goes either to one local buffer (demb, routes == nullptr) or, piece by
+// piece, straight into the owners' receive buffers over NVLink (routes: columns are relative to
+// the concatenated [n_emb * dim] embedding row).
 bool launch_interact_bwd(const void* bottom, int64_t bottom_stride, const void* emb,
                          int64_t emb_stride, int n_emb, int dim, const void* dz,
                          int64_t dz_stride, void* dbottom, int64_t dbottom_stride, void* demb,
                          int64_t demb_stride, float emb_grad_scale, int64_t batch, int sm_count,
-                         cudaStream_t stream);
+                         cudaStream_t stream, const GradRoute* routes, int n_routes,
+                         const SyncArgs& sync);
 void launch_relu_bwd_bias(void* dy, const void* y, float* db, int64_t rows, int cols,
                           cudaStream_t stream);
 bool launch_head_loss(const void* x, int K, const void* w, const void* bias, const float* labels,

@@ -15,6 +15,7 @@
 
 #include <cstdlib>
 
+#include "common.cuh"
 #include "de_b200.h"
 
 namespace de {
@@ -93,7 +94,9 @@ template <int D>
 __global__ void __launch_bounds__(kWarps * 32)
 interact_fwd_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
                     const bf16* __restrict__ emb, int64_t emb_stride, int n_emb,
-                    bf16* __restrict__ z, int64_t z_stride, int z_width, int64_t batch) {
+                    bf16* __restrict__ z, int64_t z_stride, int z_width, int64_t batch,
+                    const __grid_constant__ SyncArgs sync) {
+  sync_head(sync);  // every owner's pooled rows have landed in this rank's embedding output
   constexpr int LD = D + 8;
   constexpr int kWarpBytes = fwd_warp_bytes(D);
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -157,6 +160,7 @@ interact_fwd_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
     for (int c = n_inter + D + lane; c < z_width; c += 32) zp[c] = __float2bfloat16_rn(0.f);
     __syncwarp();
   }
+  sync_tail(sync);
 }
 
 // dF = G F with G symmetric (G_ij = dz[idx(i,j)], zero diagonal); row 0 (+ the direct copy path)
@@ -282,26 +286,58 @@ __device__ __forceinline__ void issue_sample(bf16* sF, int LD, bf16* sDz, const 
   for (int c = lane; c < dz_chunks; c += 32) cp_async16(sDz + c * 8, dz + c * 8);
 }
 
+// Per-block table of where every 16-byte chunk of a sample's embedding-gradient row goes:
+// address of the chunk for local sample 0 and the byte stride between samples.  Built once per
+// block from the route pieces (or from the single local buffer).
+struct ChunkDst {
+  unsigned long long base;
+  long long stride;
+};
+
 template <int D>
 __global__ void __launch_bounds__(kWarps * 32)
 interact_bwd_v2_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
                        const bf16* __restrict__ emb, int64_t emb_stride, int n_emb,
                        const bf16* __restrict__ dz, int64_t dz_stride, bf16* __restrict__ dbottom,
                        int64_t dbottom_stride, bf16* __restrict__ demb, int64_t demb_stride,
-                       float emb_grad_scale, int64_t batch) {
+                       float emb_grad_scale, int64_t batch,
+                       const GradRoute* __restrict__ routes, int n_routes,
+                       const __grid_constant__ SyncArgs sync) {
   constexpr int LD = D + 8;
   constexpr int LDG = 40;
   constexpr int kWarpElems = 2 * kMaxFeat * LD + 2 * kDzMax + kMaxFeat * LDG;
+  constexpr int kRowChunks = D / 8;  // 16-byte chunks per feature row
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bf16* base = reinterpret_cast<bf16*>(smem_raw) + warp * kWarpElems;
   bf16* sDz0 = base + 2 * kMaxFeat * LD;
   bf16* sG = sDz0 + 2 * kDzMax;
+  ChunkDst* sDst = reinterpret_cast<ChunkDst*>(reinterpret_cast<bf16*>(smem_raw) +
+                                               kWarps * kWarpElems);
   const int nf = n_emb + 1;
   const int n_inter = nf * (nf - 1) / 2;
   const int dz_chunks = (n_inter + D + 7) >> 3;
+  const int n_chunks = n_emb * kRowChunks;
+  // chunk routing table (all chunks are covered: the host checks that the pieces tile the row)
+  if (routes == nullptr) {
+    for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+      sDst[c].base = reinterpret_cast<unsigned long long>(demb + c * 8);
+      sDst[c].stride = demb_stride * 2;
+    }
+  } else {
+    for (int r = 0; r < n_routes; ++r) {
+      const GradRoute R = routes[r];
+      const int c0 = R.src_col >> 3, nc = R.width >> 3;
+      for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+        sDst[c0 + c].base =
+            reinterpret_cast<unsigned long long>(reinterpret_cast<bf16*>(R.dst) + R.dst_col + c * 8);
+        sDst[c0 + c].stride = R.dst_stride * 2;
+      }
+    }
+  }
   zero_pad_rows<D>(base, LD, n_emb, lane);
   zero_pad_rows<D>(base + kMaxFeat * LD, LD, n_emb, lane);
+  __syncthreads();
 
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kWarps;
   int64_t s = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
@@ -319,7 +355,7 @@ interact_bwd_v2_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
     cp_async_commit();        // possibly empty: keeps the group arithmetic uniform
     cp_async_wait_group<1>();  // everything but the prefetch just issued has landed
     __syncwarp();
-    const bf16* sF = base + cur * (kMaxFeat * LD);
+    bf16* sF = base + cur * (kMaxFeat * LD);
     const bf16* sDz = sDz0 + cur * kDzMax;
     for (int c = lane; c < kMaxFeat * LDG / 8; c += 32)
       reinterpret_cast<uint4*>(sG)[c] = make_uint4(0, 0, 0, 0);
@@ -342,8 +378,6 @@ interact_bwd_v2_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
         ldmatrix_x4(ga[mt][ks],
                     smem_u32(sG + (mt * 16 + (lane & 15)) * LDG + ks * 16 + ((lane >> 4) << 3)));
     const int cr = lane >> 2, cc = (lane & 3) << 1;
-    bf16* dbp = dbottom + s * dbottom_stride;
-    bf16* dep = demb + s * demb_stride;
 #pragma unroll 1
     for (int n0 = 0; n0 < D; n0 += 32) {
       float acc[2][4][4] = {};
@@ -362,6 +396,8 @@ interact_bwd_v2_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
           mma_bf16(acc[mt][3], ga[mt][ks], b23[2], b23[3]);
         }
       }
+      // dF overwrites F in place: columns [n0, n0 + 32) are read by this pass only (the ldmatrix
+      // loads above are warp collective, so every lane has its operands before any lane stores)
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
@@ -374,18 +410,33 @@ interact_bwd_v2_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
             if (row == 0) {
               v0 += __bfloat162float(sDz[n_inter + col]);
               v1 += __bfloat162float(sDz[n_inter + col + 1]);
-              *reinterpret_cast<__nv_bfloat162*>(dbp + col) = __floats2bfloat162_rn(v0, v1);
-            } else if (row <= n_emb) {
-              *reinterpret_cast<__nv_bfloat162*>(dep + (row - 1) * D + col) =
-                  __floats2bfloat162_rn(v0 * emb_grad_scale, v1 * emb_grad_scale);
+            } else {
+              v0 *= emb_grad_scale;
+              v1 *= emb_grad_scale;
             }
+            if (row <= n_emb)
+              *reinterpret_cast<__nv_bfloat162*>(sF + row * LD + col) =
+                  __floats2bfloat162_rn(v0, v1);
           }
         }
       }
     }
+    __syncwarp();
+    // coalesced 16-byte copy-out: row 0 -> bottom-MLP gradient, rows 1.. -> the chunk's owner
+    // (local buffer, or a peer's receive buffer over NVLink: 128-256 contiguous bytes per piece)
+    if (lane < kRowChunks)
+      *reinterpret_cast<uint4*>(dbottom + s * dbottom_stride + lane * 8) =
+          *reinterpret_cast<const uint4*>(sF + lane * 8);
+    for (int c = lane; c < n_chunks; c += 32) {
+      const int row = 1 + c / kRowChunks, ch = c - (row - 1) * kRowChunks;
+      const ChunkDst d = sDst[c];
+      *reinterpret_cast<uint4*>(d.base + static_cast<unsigned long long>(s * d.stride)) =
+          *reinterpret_cast<const uint4*>(sF + row * LD + ch * 8);
+    }
     __syncwarp();  // all lanes are done with buffer `cur` before the next iteration refills it
   }
   cp_async_wait_group<0>();
+  sync_tail(sync);  // every gradient piece of this rank is on its way to its owner
 }
 
 // dy <- dy * (y > 0) (in place) ; db[c] += sum_rows dy   (db fp32, pre-zeroed)
@@ -570,7 +621,8 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, int src_cols, bf1
 
 bool launch_interact_fwd(const void* bottom, int64_t bottom_stride, const void* emb,
                          int64_t emb_stride, int n_emb, int dim, void* z, int64_t z_stride,
-                         int z_width, int64_t batch, int sm_count, cudaStream_t stream) {
+                         int z_width, int64_t batch, int sm_count, cudaStream_t stream,
+                         const SyncArgs& sync) {
   if (n_emb + 1 > kMaxFeat || batch <= 0) return false;
   int64_t blocks = (batch + kWarps - 1) / kWarps;
   const int64_t cap = static_cast<int64_t>(sm_count) * 8;
@@ -582,7 +634,7 @@ bool launch_interact_fwd(const void* bottom, int64_t bottom_stride, const void* 
                          static_cast<int>(smem));                                                \
     interact_fwd_kernel<DD><<<static_cast<unsigned>(blocks), kWarps * 32, smem, stream>>>(       \
         reinterpret_cast<const bf16*>(bottom), bottom_stride, reinterpret_cast<const bf16*>(emb), \
-        emb_stride, n_emb, reinterpret_cast<bf16*>(z), z_stride, z_width, batch);                \
+        emb_stride, n_emb, reinterpret_cast<bf16*>(z), z_stride, z_width, batch, sync);          \
     return true;                                                                                 \
   }
   if (dim == 128) DE_IFWD(128)
@@ -597,41 +649,51 @@ bool launch_interact_bwd(const void* bottom, int64_t bottom_stride, const void* 
                          int64_t emb_stride, int n_emb, int dim, const void* dz,
                          int64_t dz_stride, void* dbottom, int64_t dbottom_stride, void* demb,
                          int64_t demb_stride, float emb_grad_scale, int64_t batch, int sm_count,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const GradRoute* routes, int n_routes,
+                         const SyncArgs& sync) {
   if (n_emb + 1 > kMaxFeat || batch <= 0 || dim % 32 != 0) return false;
   int64_t blocks = (batch + kWarps - 1) / kWarps;
   const int64_t cap = static_cast<int64_t>(sm_count) * 8;
   if (blocks > cap) blocks = cap;
-  static const bool use_v2 = [] {
-    const char* v = std::getenv("DE_B200_INTERACT_V2");
+  // DE_B200_INTERACT_V1=1 selects the single-buffered kernel (local gradient buffer only)
+  static const bool force_v1 = [] {
+    const char* v = std::getenv("DE_B200_INTERACT_V1");
     return v != nullptr && v[0] == '1';
   }();
   const int nf = n_emb + 1;
   const int dz_elems = (nf * (nf - 1) / 2 + dim + 7) / 8 * 8;
-  if (use_v2 && dz_elems <= kDzMax && dz_elems <= dz_stride && dz_stride % 8 == 0 &&
-      bottom_stride % 8 == 0 && emb_stride % 8 == 0 &&
+  const bool v2_ok =
+      dz_elems <= kDzMax && dz_elems <= dz_stride && dz_stride % 8 == 0 &&
+      bottom_stride % 8 == 0 && emb_stride % 8 == 0 && dbottom_stride % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(bottom) |
-        reinterpret_cast<uintptr_t>(emb)) & 15) == 0 && (dim == 128 || dim == 64)) {
+        reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(dbottom)) & 15) == 0 &&
+      (dim == 128 || dim == 64) &&
+      (routes != nullptr || (demb_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(demb) & 15) == 0));
+  if (routes != nullptr && !v2_ok) return false;  // pieces are pushed by the double-buffered kernel
+  const bool has_sync = sync.state != nullptr && (sync.wait_ch >= 0 || sync.signal_ch >= 0);
+  if (v2_ok && (!force_v1 || routes != nullptr || has_sync)) {
     // two resident blocks per SM, each warp streams its samples through a double buffer
     int64_t blocks2 = (batch + kWarps - 1) / kWarps;
     if (blocks2 > static_cast<int64_t>(sm_count) * 2) blocks2 = static_cast<int64_t>(sm_count) * 2;
 #define DE_IBWD2(DD)                                                                             \
   {                                                                                              \
     const size_t smem =                                                                          \
-        kWarps * (2 * kMaxFeat * (DD + 8) + 2 * kDzMax + kMaxFeat * 40) * sizeof(bf16);          \
+        kWarps * (2 * kMaxFeat * (DD + 8) + 2 * kDzMax + kMaxFeat * 40) * sizeof(bf16) +         \
+        static_cast<size_t>(n_emb) * (DD / 8) * sizeof(ChunkDst);                                \
     cudaFuncSetAttribute(interact_bwd_v2_kernel<DD>,                                             \
                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));   \
     interact_bwd_v2_kernel<DD><<<static_cast<unsigned>(blocks2), kWarps * 32, smem, stream>>>(   \
         reinterpret_cast<const bf16*>(bottom), bottom_stride, reinterpret_cast<const bf16*>(emb), \
         emb_stride, n_emb, reinterpret_cast<const bf16*>(dz), dz_stride,                         \
         reinterpret_cast<bf16*>(dbottom), dbottom_stride, reinterpret_cast<bf16*>(demb),         \
-        demb_stride, emb_grad_scale, batch);                                                     \
+        demb_stride, emb_grad_scale, batch, routes, n_routes, sync);                             \
     return true;                                                                                 \
   }
     if (dim == 128) DE_IBWD2(128)
     if (dim == 64) DE_IBWD2(64)
 #undef DE_IBWD2
   }
+  if (has_sync) return false;
 #define DE_IBWD(DD)                                                                              \
   {                                                                                              \
     const size_t smem = kWarps * (kMaxFeat * (DD + 8) + kMaxFeat * 40) * sizeof(bf16);           \

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
                   int64_t src_batch, int64_t dst_batch, int64_t dst_stride,
                   const __grid_constant__ PeerPtrs src, const __grid_constant__ PeerPtrs dst,
-                  int rot) {
+                  int rot, const __grid_constant__ SyncArgs sync) {
+  sync_head(sync);  // the ids of every requester have landed in this rank's id buffer
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
   const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
@@ -140,10 +141,14 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
               int n;
               const IdT* p = rd.sample(tc.g0 + r, n);
               const int64_t id = static_cast<int64_t>(*p) + D.id_shift;
-              if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows))
+              if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows)) {
                 acc[u] = ld_f32<VEC>(table + (D.row_base + id) * W + col);
-              else if (skip_empty)
-                ok[u] = false;
+              } else if (skip_empty) {
+                // row slices: another rank owns this id - unless it lies outside the whole
+                // table, then the first / last shard stores the zero row (flags 2 / 4)
+                const bool caught = ((D.flags & 2) && id < 0) || ((D.flags & 4) && id >= D.sub_rows);
+                if (!caught) ok[u] = false;
+              }
             }
           }
 #pragma unroll
@@ -195,147 +200,7 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
       }
     }
   }
-}
-
-// ---- one-hot forward with TMA bulk row copies (DE_B200_LOOKUP_BULK=1; EXPERIMENTAL, written
-// after the round-1 GPU budget was spent).  The LSU version above keeps at most
-// kUnroll x 512 B per lane group in flight and pays registers for it (80 regs -> 3 CTAs/SM, 69 %
-// of the DRAM roofline).  Here every lane asks the TMA engine for its sample's whole row
-// (`cp.async.bulk` global -> shared, completion counted in bytes on an mbarrier), two tiles of 32
-// rows per warp are in flight (32 KB of a 128-wide fp32 table per warp, no registers), and the
-// warp then streams the rows from shared memory to the requester's output row (peer memory)
-// with the same coalesced bf16 / fp32 stores as above.
-constexpr int kBulkWarps = 4;      // warps per block
-constexpr int kBulkStages = 2;     // tiles in flight per warp
-constexpr int kBulkMaxWidth = 128; // fp32 columns per row staged in shared memory
-
-__device__ __forceinline__ uint32_t smem_u32_addr(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void bulk_mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void bulk_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32_addr(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "BULK_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra BULK_DONE;\n"
-      "bra BULK_WAIT;\n"
-      "BULK_DONE:\n"
-      "}\n" ::"r"(smem_u32_addr(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
-                                              uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32_addr(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(smem_u32_addr(bar))
-      : "memory");
-}
-
-template <typename IdT, typename OutT>
-__global__ void __launch_bounds__(kBulkWarps * 32)
-lookup_fwd_bulk_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
-                       int64_t src_batch, int64_t dst_batch, int64_t dst_stride,
-                       const __grid_constant__ PeerPtrs src, const __grid_constant__ PeerPtrs dst,
-                       int rot) {
-  extern __shared__ __align__(128) unsigned char bulk_smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  // per warp: kBulkStages x [32 rows][kBulkMaxWidth] fp32, then the barriers of all warps
-  float* rows = reinterpret_cast<float*>(bulk_smem) +
-                static_cast<size_t>(wib) * kBulkStages * kTile * kBulkMaxWidth;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(
-                       bulk_smem + static_cast<size_t>(kBulkWarps) * kBulkStages * kTile *
-                                       kBulkMaxWidth * sizeof(float)) +
-                   wib * kBulkStages;
-  if (lane == 0) {
-    for (int s = 0; s < kBulkStages; ++s) bulk_mbar_init(&bars[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-
-  const int64_t warp = static_cast<int64_t>(blockIdx.x) * kBulkWarps + wib;
-  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kBulkWarps;
-  const int n_dst = static_cast<int>((batch + dst_batch - 1) / dst_batch);
-  const int64_t tiles_per_dst = (dst_batch + kTile - 1) / kTile;
-  const int64_t total = static_cast<int64_t>(n_inputs) * n_dst * tiles_per_dst;
-
-  // issue the row copies of tile t into stage s (every lane: the row of its own sample)
-  auto issue = [&](int64_t t, int s) {
-    const TileCoord tc = decode_tile(t, n_inputs, n_dst, tiles_per_dst, batch, dst_batch, rot);
-    const InputDesc& D = descs[tc.f];
-    const int W = D.width;
-    const uint32_t row_bytes = static_cast<uint32_t>(W) * 4u;
-    float* stage = rows + static_cast<size_t>(s) * kTile * kBulkMaxWidth;
-    const float* gsrc = nullptr;
-    if (lane < tc.nsamp) {
-      const IdReader<IdT> rd = make_reader<IdT>(D, src, src_batch);
-      int n;
-      const IdT* p = rd.sample(tc.g0 + lane, n);
-      const int64_t id = static_cast<int64_t>(*p) + D.id_shift;
-      if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows))
-        gsrc = reinterpret_cast<const float*>(D.table) + (D.row_base + id) * W;
-    }
-    const unsigned valid = __ballot_sync(0xffffffffu, gsrc != nullptr);
-    // the previous readers of this stage are done (__syncwarp at the end of consume); order
-    // their generic-proxy reads before the async-proxy writes that follow
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (lane == 0) bulk_mbar_expect_tx(&bars[s], __popc(valid) * row_bytes);
-    __syncwarp();
-    if (gsrc != nullptr) {
-      bulk_copy_g2s(stage + lane * kBulkMaxWidth, gsrc, row_bytes, &bars[s]);
-    } else if (lane < tc.nsamp) {
-      for (int c = 0; c < W; c += 4)  // out-of-range id: the sample pools to zero
-        *reinterpret_cast<float4*>(stage + lane * kBulkMaxWidth + c) = make_float4(0, 0, 0, 0);
-    }
-  };
-
-  uint32_t parity = 0;  // bit s: phase parity of stage s
-  int64_t t = warp;
-  int s = 0;
-  if (t < total) issue(t, 0);
-  for (; t < total; t += n_warps, s ^= 1) {
-    const int64_t tn = t + n_warps;
-    if (tn < total) issue(tn, s ^ 1);  // keep the next tile's rows in flight
-    bulk_mbar_wait(&bars[s], (parity >> s) & 1u);
-    parity ^= 1u << s;
-    __syncwarp();  // zero-filled rows of other lanes are visible too
-    const TileCoord tc = decode_tile(t, n_inputs, n_dst, tiles_per_dst, batch, dst_batch, rot);
-    const InputDesc& D = descs[tc.f];
-    const int W = D.width;
-    const float* stage = rows + static_cast<size_t>(s) * kTile * kBulkMaxWidth;
-    OutT* out_base = reinterpret_cast<OutT*>(dst.p[tc.d]);
-    const int64_t i0 = tc.g0 - static_cast<int64_t>(tc.d) * dst_batch;
-    // lane = 4 columns; one row per pass when W == 128, several rows per pass for narrow tables
-    const int nvec = W >> 2;
-    const int lpr = min(32, pow2_ceil(nvec));
-    const int rpw = 32 / lpr;
-    const int sub = lane / lpr, li = lane - sub * lpr;
-    for (int r0 = 0; r0 < tc.nsamp; r0 += rpw) {
-      const int r = r0 + sub;
-      if (r < tc.nsamp) {
-        for (int cv = li; cv < nvec; cv += lpr) {
-          const float4 v = *reinterpret_cast<const float4*>(stage + r * kBulkMaxWidth + cv * 4);
-          FVec<4> x;
-          x.v[0] = v.x;
-          x.v[1] = v.y;
-          x.v[2] = v.z;
-          x.v[3] = v.w;
-          st_act<OutT, 4>(out_base + (i0 + r) * dst_stride + D.dst_col + cv * 4, x);
-        }
-      }
-    }
-    __syncwarp();  // all lanes are done with stage s before it is refilled
-  }
+  sync_tail(sync);  // every pooled row of this rank is on its way: tell the requesters
 }
 
 // =============================================================================== backward
@@ -347,7 +212,9 @@ __global__ void __launch_bounds__(kThreads, VEC == 8 ? 2 : kBlocksPerSM)
 scatter_add_bwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
                        int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
                        const __grid_constant__ PeerPtrs src, const __grid_constant__ PeerPtrs grad,
-                       int rot, float scale, const float* __restrict__ scale_ptr) {
+                       int rot, float scale, const float* __restrict__ scale_ptr,
+                       const __grid_constant__ SyncArgs sync) {
+  sync_head(sync);  // every requester's gradient rows have landed in the receive buffer
   if (scale_ptr != nullptr) scale *= *scale_ptr;  // device-resident lr (CUDA-graph friendly)
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
@@ -427,78 +294,7 @@ scatter_add_bwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_
       }
     }
   }
-}
-
-// ---- tiny tables (DE_B200_TINY_TABLES=1; EXPERIMENTAL, written after the round-1 GPU budget
-// was spent).  A table with a handful of rows receives `batch` reductions per step on the same
-// few L2 lines: ncu of the kernel above shows the atomic unit of the busiest L2 slice at 56 %
-// while the average slice sits at 17 %.  Here one block owns a chunk of samples of ONE tiny
-// one-hot input, accumulates the gradient rows in shared memory (fp32 smem atomics), and issues
-// one vector RED per touched row and 4 columns: chunk-size times fewer L2 atomics.
-constexpr int kTinyChunk = 2048;  // samples per block
-constexpr int kTinyUnroll = 4;
-
-template <typename IdT, typename GradT>
-__global__ void __launch_bounds__(kThreads)
-tiny_scatter_add_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
-                        int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
-                        const __grid_constant__ PeerPtrs src,
-                        const __grid_constant__ PeerPtrs grad, float scale,
-                        const float* __restrict__ scale_ptr, int n_chunks) {
-  extern __shared__ float s_acc[];  // [sub_rows][width]
-  if (scale_ptr != nullptr) scale *= *scale_ptr;
-  const int f = blockIdx.x / n_chunks;
-  const int chunk = blockIdx.x - f * n_chunks;
-  if (f >= n_inputs) return;
-  const InputDesc D = descs[f];
-  const int W = D.width;
-  const int rows = static_cast<int>(D.sub_rows);
-  for (int i = threadIdx.x; i < rows * W; i += kThreads) s_acc[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const IdReader<IdT> rd = make_reader<IdT>(D, src, src_batch);
-  const int64_t g_lo = static_cast<int64_t>(chunk) * kTinyChunk;
-  const int64_t g_hi = min(batch, g_lo + kTinyChunk);
-  // warp per sample, lane per 4 columns (columns beyond 128 in further passes)
-  for (int64_t g0 = g_lo + warp; g0 < g_hi; g0 += kWarpsPerBlock * kTinyUnroll) {
-    for (int c0 = lane * 4; c0 < W; c0 += 128) {
-      FVec<4> gv[kTinyUnroll];
-      int64_t id[kTinyUnroll];
-#pragma unroll
-      for (int u = 0; u < kTinyUnroll; ++u) {
-        const int64_t g = g0 + static_cast<int64_t>(u) * kWarpsPerBlock;
-        id[u] = -1;
-        if (g < g_hi) {
-          int n;
-          const IdT* p = rd.sample(g, n);
-          id[u] = static_cast<int64_t>(p[0]) + D.id_shift;
-          const int64_t d = g / grad_batch;
-          const int64_t i = g - d * grad_batch;
-          gv[u] = ld_act<GradT, 4>(reinterpret_cast<const GradT*>(grad.p[d]) + i * grad_stride +
-                                   D.dst_col + c0);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kTinyUnroll; ++u) {
-        if (static_cast<uint64_t>(id[u]) < static_cast<uint64_t>(rows)) {
-          float* a = s_acc + static_cast<int>(id[u]) * W + c0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) atomicAdd(a + k, gv[u].v[k] * scale);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  float* table = reinterpret_cast<float*>(const_cast<void*>(D.table));
-  const int nvec = W >> 2;
-  for (int i = threadIdx.x; i < rows * nvec; i += kThreads) {
-    const int r = i / nvec, c = (i - r * nvec) << 2;
-    FVec<4> v;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v.v[k] = s_acc[r * W + c + k];
-    if (v.v[0] != 0.f || v.v[1] != 0.f || v.v[2] != 0.f || v.v[3] != 0.f)
-      red_add_f32<4>(table + (D.row_base + r) * W + c, v);
-  }
+  sync_tail(sync);  // ids and gradient rows are consumed: the requesters may overwrite them
 }
 
 // DE_B200_EMB_BLOCKS_PER_SM=1..4 caps the resident CTAs per SM of the persistent lookup / scatter
@@ -531,128 +327,71 @@ int64_t count_tiles(int n_inputs, int64_t batch, int64_t dst_batch) {
 
 #define DE_DISPATCH_FWD(IdT, OutT, VEC)                                                        \
   lookup_fwd_kernel<IdT, OutT, VEC><<<grid, kThreads, 0, stream>>>(                            \
-      descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src, dst, rot)
+      descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src, dst, rot, sync)
+#define DE_DISPATCH_FWD_T(IdT, VEC)                                                            \
+  do {                                                                                         \
+    if (act_dtype == 1) DE_DISPATCH_FWD(IdT, __nv_bfloat16, VEC);                              \
+    else if (act_dtype == 2) DE_DISPATCH_FWD(IdT, __half, VEC);                                \
+    else DE_DISPATCH_FWD(IdT, float, VEC);                                                     \
+  } while (0)
 
 void launch_lookup_fwd(const InputDesc* descs, int n_inputs, int64_t batch, int64_t src_batch,
                        int64_t dst_batch, int64_t dst_stride, const PeerPtrs& src,
-                       const PeerPtrs& dst, int rot, bool ids64, bool out_bf16, bool vec4,
-                       int sm_count, cudaStream_t stream) {
-  if (n_inputs <= 0 || batch <= 0) return;
+                       const PeerPtrs& dst, int rot, bool ids64, int act_dtype, bool vec4,
+                       int sm_count, cudaStream_t stream, const SyncArgs& sync) {
+  if (n_inputs <= 0 || batch <= 0) {
+    launch_sync_only(sync, stream);  // keep the signalling protocol in step
+    return;
+  }
   const int grid = grid_for(count_tiles(n_inputs, batch, dst_batch), sm_count, kBlocksPerSM);
   if (vec4) {
-    if (ids64) {
-      if (out_bf16) DE_DISPATCH_FWD(int64_t, __nv_bfloat16, 4);
-      else DE_DISPATCH_FWD(int64_t, float, 4);
-    } else {
-      if (out_bf16) DE_DISPATCH_FWD(int32_t, __nv_bfloat16, 4);
-      else DE_DISPATCH_FWD(int32_t, float, 4);
-    }
+    if (ids64) DE_DISPATCH_FWD_T(int64_t, 4);
+    else DE_DISPATCH_FWD_T(int32_t, 4);
   } else {
-    if (ids64) {
-      if (out_bf16) DE_DISPATCH_FWD(int64_t, __nv_bfloat16, 1);
-      else DE_DISPATCH_FWD(int64_t, float, 1);
-    } else {
-      if (out_bf16) DE_DISPATCH_FWD(int32_t, __nv_bfloat16, 1);
-      else DE_DISPATCH_FWD(int32_t, float, 1);
-    }
+    if (ids64) DE_DISPATCH_FWD_T(int64_t, 1);
+    else DE_DISPATCH_FWD_T(int32_t, 1);
   }
 }
 
 #define DE_DISPATCH_BWD(IdT, GradT, VEC)                                                       \
   scatter_add_bwd_kernel<IdT, GradT, VEC><<<grid, kThreads, 0, stream>>>(                      \
-      descs, n_inputs, batch, src_batch, grad_batch, grad_stride, src, grad, rot, scale, scale_ptr)
+      descs, n_inputs, batch, src_batch, grad_batch, grad_stride, src, grad, rot, scale,       \
+      scale_ptr, sync)
+#define DE_DISPATCH_BWD_T(IdT, VEC)                                                            \
+  do {                                                                                         \
+    if (act_dtype == 1) DE_DISPATCH_BWD(IdT, __nv_bfloat16, VEC);                              \
+    else if (act_dtype == 2) DE_DISPATCH_BWD(IdT, __half, VEC);                                \
+    else DE_DISPATCH_BWD(IdT, float, VEC);                                                     \
+  } while (0)
 
 void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch, int64_t src_batch,
                             int64_t grad_batch, int64_t grad_stride, const PeerPtrs& src,
                             const PeerPtrs& grad, int rot, float scale, const float* scale_ptr,
-                            bool ids64, bool grad_bf16, bool vec4, int sm_count,
-                            cudaStream_t stream, bool vec8) {
-  if (n_inputs <= 0 || batch <= 0) return;
+                            bool ids64, int act_dtype, bool vec4, int sm_count,
+                            cudaStream_t stream, bool vec8, const SyncArgs& sync) {
+  if (n_inputs <= 0 || batch <= 0) {
+    launch_sync_only(sync, stream);
+    return;
+  }
   const int grid = grid_for(count_tiles(n_inputs, batch, grad_batch), sm_count, kBlocksPerSM);
-  if (vec8 && grad_bf16) {
-    // 16-byte gradient loads: 8 columns per lane, two rows per warp instruction (peer pulls)
-    if (ids64) DE_DISPATCH_BWD(int64_t, __nv_bfloat16, 8);
-    else DE_DISPATCH_BWD(int32_t, __nv_bfloat16, 8);
+  if (vec8 && act_dtype != 0) {
+    // 16-byte gradient loads: 8 columns per lane, two rows per warp instruction
+    if (act_dtype == 1) {
+      if (ids64) DE_DISPATCH_BWD(int64_t, __nv_bfloat16, 8);
+      else DE_DISPATCH_BWD(int32_t, __nv_bfloat16, 8);
+    } else {
+      if (ids64) DE_DISPATCH_BWD(int64_t, __half, 8);
+      else DE_DISPATCH_BWD(int32_t, __half, 8);
+    }
     return;
   }
   if (vec4) {
-    if (ids64) {
-      if (grad_bf16) DE_DISPATCH_BWD(int64_t, __nv_bfloat16, 4);
-      else DE_DISPATCH_BWD(int64_t, float, 4);
-    } else {
-      if (grad_bf16) DE_DISPATCH_BWD(int32_t, __nv_bfloat16, 4);
-      else DE_DISPATCH_BWD(int32_t, float, 4);
-    }
+    if (ids64) DE_DISPATCH_BWD_T(int64_t, 4);
+    else DE_DISPATCH_BWD_T(int32_t, 4);
   } else {
-    if (ids64) {
-      if (grad_bf16) DE_DISPATCH_BWD(int64_t, __nv_bfloat16, 1);
-      else DE_DISPATCH_BWD(int64_t, float, 1);
-    } else {
-      if (grad_bf16) DE_DISPATCH_BWD(int32_t, __nv_bfloat16, 1);
-      else DE_DISPATCH_BWD(int32_t, float, 1);
-    }
+    if (ids64) DE_DISPATCH_BWD_T(int64_t, 1);
+    else DE_DISPATCH_BWD_T(int32_t, 1);
   }
-}
-
-// One-hot inputs of tables with at most max_rows rows (width % 4 == 0): shared-memory
-// pre-reduction per 2048-sample chunk, then one vector RED per touched row segment.
-bool launch_tiny_scatter_add(const InputDesc* descs, int n_inputs, int64_t batch,
-                             int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
-                             const PeerPtrs& src, const PeerPtrs& grad, float scale,
-                             const float* scale_ptr, bool ids64, bool grad_bf16, int max_rows,
-                             int max_width, cudaStream_t stream) {
-  if (n_inputs <= 0 || batch <= 0) return true;
-  const size_t smem = static_cast<size_t>(max_rows) * max_width * sizeof(float);
-  if (smem > 96 * 1024 || (max_width & 3)) return false;
-  const int n_chunks = static_cast<int>((batch + kTinyChunk - 1) / kTinyChunk);
-  const unsigned grid = static_cast<unsigned>(n_inputs) * n_chunks;
-#define DE_TINY(IdT, GradT)                                                                       \
-  {                                                                                               \
-    cudaFuncSetAttribute(tiny_scatter_add_kernel<IdT, GradT>,                                     \
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));    \
-    tiny_scatter_add_kernel<IdT, GradT><<<grid, kThreads, smem, stream>>>(                        \
-        descs, n_inputs, batch, src_batch, grad_batch, grad_stride, src, grad, scale, scale_ptr,  \
-        n_chunks);                                                                                \
-  }
-  if (ids64) {
-    if (grad_bf16) DE_TINY(int64_t, __nv_bfloat16) else DE_TINY(int64_t, float)
-  } else {
-    if (grad_bf16) DE_TINY(int32_t, __nv_bfloat16) else DE_TINY(int32_t, float)
-  }
-#undef DE_TINY
-  return cudaGetLastError() == cudaSuccess;
-}
-
-// One-hot inputs (hotness 1, no CSR, no skip-empty flag), widths % 4 == 0 and <= 128, destination
-// columns % 4 == 0: the caller checks the descriptors, this only launches.
-bool launch_lookup_fwd_bulk(const InputDesc* descs, int n_inputs, int64_t batch,
-                            int64_t src_batch, int64_t dst_batch, int64_t dst_stride,
-                            const PeerPtrs& src, const PeerPtrs& dst, int rot, bool ids64,
-                            bool out_bf16, int sm_count, cudaStream_t stream) {
-  if (n_inputs <= 0 || batch <= 0) return true;
-  const size_t smem = static_cast<size_t>(kBulkWarps) * kBulkStages * kTile * kBulkMaxWidth *
-                          sizeof(float) +
-                      kBulkWarps * kBulkStages * sizeof(uint64_t);
-  const int64_t tiles = count_tiles(n_inputs, batch, dst_batch);
-  int64_t blocks = (tiles + kBulkWarps - 1) / kBulkWarps;
-  const int64_t cap = static_cast<int64_t>(sm_count);  // 128 KB of staging: one CTA per SM
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-#define DE_BULK(IdT, OutT)                                                                        \
-  {                                                                                               \
-    cudaFuncSetAttribute(lookup_fwd_bulk_kernel<IdT, OutT>,                                       \
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));    \
-    lookup_fwd_bulk_kernel<IdT, OutT><<<static_cast<unsigned>(blocks), kBulkWarps * 32, smem,     \
-                                        stream>>>(descs, n_inputs, batch, src_batch, dst_batch,   \
-                                                  dst_stride, src, dst, rot);                     \
-  }
-  if (ids64) {
-    if (out_bf16) DE_BULK(int64_t, __nv_bfloat16) else DE_BULK(int64_t, float)
-  } else {
-    if (out_bf16) DE_BULK(int32_t, __nv_bfloat16) else DE_BULK(int32_t, float)
-  }
-#undef DE_BULK
-  return cudaGetLastError() == cudaSuccess;
 }
 
 }  // namespace de

@@ -82,6 +82,16 @@ __global__ void finish_segments_kernel(int64_t* seg_start, const int64_t* n_uniq
   if (threadIdx.x == 0 && blockIdx.x == 0) seg_start[*n_unique] = n;
 }
 
+// Adam bias corrections from a device-resident step count (the host scalars baked into a captured
+// CUDA graph would freeze at their capture-time values).
+__device__ __forceinline__ void resolve_step(OptimizerArgs& opt) {
+  if (opt.step_ptr != nullptr && opt.kind == kOptAdam) {
+    const float t = *opt.step_ptr;
+    opt.bias1 = 1.f - powf(opt.beta1, t);
+    opt.bias2 = 1.f - powf(opt.beta2, t);
+  }
+}
+
 // ------------------------------------------------------------------ per-row optimizer apply
 template <int VEC>
 __device__ __forceinline__ void apply_update(const TableDesc& T, const OptimizerArgs& opt,
@@ -187,6 +197,7 @@ segment_update_kernel(const InputDesc* __restrict__ descs, const TableDesc* __re
                       float* __restrict__ emit_rows, int emit_width) {
   OptimizerArgs opt = opt_in;
   if (opt.lr_ptr != nullptr) opt.lr = *opt.lr_ptr;
+  resolve_step(opt);
   const int64_t n_unique = *n_unique_p;
   const int64_t sentinel = tables[n_tables - 1].key_base + tables[n_tables - 1].rows;
   const int lane = threadIdx.x & 31;
@@ -350,6 +361,7 @@ balanced_update_kernel(const InputDesc* __restrict__ descs, const TableDesc* __r
                        int scratch_width) {
   OptimizerArgs opt = opt_in;
   if (opt.lr_ptr != nullptr) opt.lr = *opt.lr_ptr;
+  resolve_step(opt);
   const int64_t n_unique = *n_unique_p;
   const int64_t sentinel = tables[n_tables - 1].key_base + tables[n_tables - 1].rows;
   const int lane = threadIdx.x & 31;
@@ -442,6 +454,7 @@ finalize_crossing_kernel(const TableDesc* __restrict__ tables, int n_tables, int
                          int scratch_width) {
   OptimizerArgs opt = opt_in;
   if (opt.lr_ptr != nullptr) opt.lr = *opt.lr_ptr;
+  resolve_step(opt);
   const int64_t sentinel = tables[n_tables - 1].key_base + tables[n_tables - 1].rows;
   const int lane = threadIdx.x & 31;
   const int rpw = 32 / lpr;
@@ -549,7 +562,7 @@ void launch_segment_update(const InputDesc* descs, const TableDesc* tables, int 
                            const PeerPtrs& grad, const int64_t* sorted_keys,
                            const uint32_t* sorted_items, const int64_t* seg_start,
                            const int64_t* n_unique, int64_t n_items, const OptimizerArgs& opt,
-                           int64_t* emit_keys, float* emit_rows, int max_width, bool grad_bf16,
+                           int64_t* emit_keys, float* emit_rows, int max_width, int act_dtype,
                            bool vec4, int sm_count, cudaStream_t stream) {
   const int emit_width = max_width;
   if (n_items <= 0 || n_tables <= 0) return;
@@ -565,10 +578,12 @@ void launch_segment_update(const InputDesc* descs, const TableDesc* tables, int 
   const int64_t warps = (n_items + rpw - 1) / rpw;
   const int grid = grid_cap(warps, sm_count, 8);
   if (vec4) {
-    if (grad_bf16) DE_DISPATCH_SEG(__nv_bfloat16, 4);
+    if (act_dtype == 1) DE_DISPATCH_SEG(__nv_bfloat16, 4);
+    else if (act_dtype == 2) DE_DISPATCH_SEG(__half, 4);
     else DE_DISPATCH_SEG(float, 4);
   } else {
-    if (grad_bf16) DE_DISPATCH_SEG(__nv_bfloat16, 1);
+    if (act_dtype == 1) DE_DISPATCH_SEG(__nv_bfloat16, 1);
+    else if (act_dtype == 2) DE_DISPATCH_SEG(__half, 1);
     else DE_DISPATCH_SEG(float, 1);
   }
 }
@@ -582,7 +597,7 @@ bool launch_balanced_update(const InputDesc* descs, const TableDesc* tables, int
                             const uint32_t* sorted_items, int64_t n_items,
                             const int64_t* seg_start, const int64_t* n_unique,
                             const OptimizerArgs& opt, float* scratch, int scratch_width,
-                            int max_width, bool grad_bf16, int sm_count, cudaStream_t stream) {
+                            int max_width, int act_dtype, int sm_count, cudaStream_t stream) {
   if (n_items <= 0 || n_tables <= 0) return true;
   if (max_width > 128 || max_width % 4 || scratch_width % 4 || opt.kind == kOptEmit) return false;
   int lpr = 1;
@@ -590,8 +605,12 @@ bool launch_balanced_update(const InputDesc* descs, const TableDesc* tables, int
   const int rpw = 32 / lpr;
   const int64_t n_chunks = (n_items + kChunk - 1) / kChunk;
   const int grid = grid_cap((n_chunks + rpw - 1) / rpw, sm_count, 8);
-  if (grad_bf16)
+  if (act_dtype == 1)
     balanced_update_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(
+        descs, tables, n_tables, lpr, batch, grad_batch, grad_stride, grad, sorted_keys,
+        sorted_items, n_items, seg_start, n_unique, opt, scratch, scratch_width);
+  else if (act_dtype == 2)
+    balanced_update_kernel<__half><<<grid, kThreads, 0, stream>>>(
         descs, tables, n_tables, lpr, batch, grad_batch, grad_stride, grad, sorted_keys,
         sorted_items, n_items, seg_start, n_unique, opt, scratch, scratch_width);
   else

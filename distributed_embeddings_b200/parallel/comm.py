@@ -20,9 +20,17 @@ import torch.distributed as dist
 
 from ..ops import _native
 
-# ~2 s at 2 GHz before a flag wait gives up and raises the error flag
-DEFAULT_TIMEOUT_CYCLES = int(os.environ.get("DE_B200_FLAG_TIMEOUT_CYCLES", str(4_000_000_000)))
+# Cycles a device-side flag wait may spin before the watchdog records the missing peer in
+# host-mapped memory and traps the kernel (~60 s at 2 GHz; 0 = wait forever).  A timeout is
+# fatal by design: continuing past a lost peer would consume stale ids / gradients and corrupt
+# the tables silently, whereas a trapped kernel surfaces as a CUDA error on every later call.
+DEFAULT_TIMEOUT_CYCLES = int(os.environ.get("DE_B200_FLAG_TIMEOUT_CYCLES", str(120_000_000_000)))
 NUM_CHANNELS = 16
+# signalling channels of the fused embedding engine (kernels wait / signal on them, see
+# ops/csrc/common.cuh sync_head / sync_tail); legacy two-way barriers use 8..10, the dense
+# all-reduce 14..15
+CH_IDS, CH_OUT, CH_GRAD, CH_CONSUMED = 0, 1, 2, 3
+CH_BARRIER0 = 8
 
 
 def dist_ready() -> bool:
@@ -150,6 +158,9 @@ class CommContext:
     self.signal: Optional[SymmetricBuffer] = None
     self._epochs: Dict[int, torch.Tensor] = {}
     self.error_flag: Optional[torch.Tensor] = None
+    self.error_ptr = 0
+    self.sync_state: Optional[torch.Tensor] = None
+    self.sync_handle = -1
     self.timeout_cycles = DEFAULT_TIMEOUT_CYCLES
     # Peer mappings need every rank on one host with peer access; otherwise (multi-node jobs,
     # PCIe boxes without P2P) the context stays usable for bookkeeping and callers fall back to
@@ -207,11 +218,31 @@ class CommContext:
 
   def _init_p2p(self):
     with torch.cuda.device(self.device):
+      ops = _native.require()
       self.signal = SymmetricBuffer(self, NUM_CHANNELS * _native.MAX_PEERS * 4, "signal_pad")
-      self.error_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+      # watchdog word in pinned host memory: still readable after a kernel trapped
+      self.error_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+      self.error_ptr = int(ops.host_device_pointer(self.error_flag))
+      # wait / signal epochs + block counters of the signalling protocol (device resident)
+      self.sync_state = torch.zeros(_native.SYNC_STATE_WORDS, dtype=torch.int32,
+                                    device=self.device)
+      self.sync_handle = int(ops.sync_ctx_create(self.signal.ptrs, self.sync_state, self.rank,
+                                                 self.world_size, self.timeout_cycles,
+                                                 self.error_ptr))
       if self.world_size > 1:
         dist.barrier(group=self.group)
       self.p2p = True
+
+  def sync(self, wait: int = -1, wait_abs: int = -1, signal: int = -1, slot: Optional[int] = None):
+    """Signalling spec for a native op (``int[] sync``): the kernel waits at its head for every
+    peer's signal on channel ``wait`` (and/or until the peers have caught up with this rank's own
+    signals on ``wait_abs``) and publishes ``signal`` to every peer from its tail.  Empty list
+    on a single rank."""
+    if self.world_size == 1 or not self.p2p:
+      return []
+    if slot is None:
+      slot = signal if signal >= 0 else NUM_CHANNELS + max(wait, wait_abs, 0)
+    return [self.sync_handle, int(wait), int(wait_abs), int(signal), int(slot)]
 
   def epoch(self, channel: int) -> torch.Tensor:
     """Device-resident epoch words of a channel ([0] epoch, [1] block counter): kernels bump them
@@ -254,11 +285,12 @@ class CommContext:
       dist.barrier(group=self.group)
       return
     _native.ops().barrier(self.signal.ptrs, self.epoch(channel), self.rank, self.world_size,
-                          channel, self.timeout_cycles, self.error_flag)
+                          channel, self.timeout_cycles, self.error_ptr)
 
   def allreduce_(self, buf: SymmetricBuffer, n_elems: int, dtype: torch.dtype, scale: float = 1.0,
-                 channel: int = 15, byte_offset: int = 0, mc_ptr: int = 0):
-    """In-place sum (x scale) over all ranks of a symmetric buffer; one kernel, no NCCL."""
+                 channel: int = 15, byte_offset: int = 0, mc_ptr: int = 0, max_blocks: int = 0):
+    """In-place sum (x scale) over all ranks of a symmetric buffer; one kernel, no NCCL.
+    ``max_blocks`` > 0 caps the grid (use it when the all-reduce overlaps other kernels)."""
     if self.world_size == 1:
       if scale != 1.0:
         buf.view(dtype, (n_elems,), byte_offset).mul_(scale)
@@ -269,13 +301,14 @@ class CommContext:
         mc_ptr += byte_offset
     _native.ops().allreduce(buf.peer_ptrs(byte_offset), self.signal.ptrs, self.epoch(channel),
                             self.rank, self.world_size, n_elems, float(scale),
-                            dtype == torch.bfloat16, channel, self.timeout_cycles, self.error_flag,
-                            mc_ptr)
+                            dtype == torch.bfloat16, channel, self.timeout_cycles, self.error_ptr,
+                            mc_ptr, int(max_blocks))
 
   def check_errors(self):
-    """Host check of the watchdog flag (synchronises; call outside hot loops)."""
+    """Host check of the watchdog word (pinned host memory: no device synchronisation, and still
+    readable after a timed-out kernel trapped the context)."""
     if self.error_flag is not None:
-      v = int(self.error_flag.item())
+      v = int(self.error_flag[0])
       if v != 0:
         raise RuntimeError(
             f"rank {self.rank}: peer flag wait timed out waiting for rank {v - 1} - a rank is "

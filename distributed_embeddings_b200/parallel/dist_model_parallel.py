@@ -24,6 +24,7 @@ import torch.distributed as dist
 from torch import nn
 
 from ..layers.embedding import Embedding, config_from_layer
+from ..ops import embedding_lookup_ops as elo
 from ..ops.ragged import RaggedIds, SparseIds
 from ..utils import initializers
 from .comm import dist_ready
@@ -437,7 +438,9 @@ class DistributedEmbedding(nn.Module):
       from .fused import FusedEngine  # pylint: disable=import-outside-toplevel
       if self._engine is None:
         self._engine = FusedEngine(self)
-      if self._engine.supports(inputs):
+      # a forward whose backward is still outstanding owns the engine's buffers: further calls
+      # (two-tower models, gradient accumulation over several forwards) take the torch back end
+      if self._engine.supports(inputs) and not self._engine.busy():
         return self._engine.forward(inputs, concat)
     outs = self._forward_torch(inputs)
     return torch.cat(outs, dim=1) if concat else outs
@@ -522,7 +525,23 @@ class DistributedEmbedding(nn.Module):
     rows are masked afterwards (one id per sample only - pooling inside a user layer cannot be
     masked)."""
     if isinstance(layer, Embedding):
-      return layer(ids)
+      if layer.use_custom_kernel:
+        return layer(ids)
+      # library-path layers (F.embedding / embedding_bag) reject the shifted ids that fall
+      # outside the shard; the masking lookup (kernel on CUDA, oracle on CPU) zero-fills them
+      # like TF's gather does for the reference
+      w = layer.embeddings
+      ids = ids.to(w.device)
+      shape = None
+      if ids.dim() == 1:
+        shape, ids = (ids.shape[0], w.shape[1]), ids.reshape(-1, 1)
+      elif ids.dim() > 2:
+        lead = tuple(ids.shape[:-1]) if layer.combiner is not None else tuple(ids.shape)
+        shape, ids = lead + (w.shape[1],), ids.reshape(-1, ids.shape[-1])
+      elif layer.combiner is None:
+        shape = tuple(ids.shape) + (w.shape[1],)
+      out = elo.embedding_lookup(w, ids, combiner=layer.combiner, sparse_grad=layer.sparse_grad)
+      return out.reshape(shape) if shape is not None else out
     if ids.dim() != 1:
       raise ValueError("row-sliced user-defined layers support one id per sample only")
     rows = _layer_weight(layer).shape[0]

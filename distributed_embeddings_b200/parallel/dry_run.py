@@ -31,7 +31,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from ..ops._native import INPUT_DESC, MAX_PEERS, TABLE_DESC
+from ..ops._native import GRAD_ROUTE, INPUT_DESC, MAX_PEERS, TABLE_DESC
 from . import fused as _fused
 
 
@@ -144,6 +144,14 @@ class DryCtx:
     if self.world_size > 1:
       self.world.barrier()
 
+  def sync(self, wait: int = -1, wait_abs: int = -1, signal: int = -1, slot=None):
+    """Signalling spec of the interpreter: an op that *waits* rendezvouses with all ranks first.
+    Every rank issues the same op sequence and its own signalling op precedes its waiting op in
+    program order, so a barrier at each wait gives exactly the ordering the flag words give."""
+    if self.world_size == 1:
+      return []
+    return [-1, int(wait), int(wait_abs), int(signal), 0]
+
   def check_errors(self):
     pass
 
@@ -187,6 +195,17 @@ class DryOps:
     self.calls[name] = self.calls.get(name, 0) + 1
     self._sync_registry()
 
+  def _wait(self, sync):
+    """Head wait of a kernel (see DryCtx.sync)."""
+    if sync and (sync[1] >= 0 or sync[2] >= 0):
+      self.world.barrier()
+
+  _ADT = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}
+
+  def sync_only(self, sync):
+    self._count("sync_only")
+    self._wait(sync)
+
   @staticmethod
   def _descs(blob: torch.Tensor, n: int, dtype=INPUT_DESC) -> np.ndarray:
     return np.frombuffer(blob.numpy().tobytes(), dtype=dtype)[:int(n)]
@@ -224,10 +243,11 @@ class DryOps:
 
   # -- forward -------------------------------------------------------------------------------
   def lookup_fwd(self, descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src_ptrs,
-                 dst_ptrs, rot, ids64, out_bf16, vec4):
+                 dst_ptrs, rot, ids64, act_dtype, vec4, sync):
     self._count("lookup_fwd")
-    odt = torch.bfloat16 if out_bf16 else torch.float32
-    osz = 2 if out_bf16 else 4
+    self._wait(sync)
+    odt = self._ADT[int(act_dtype)]
+    osz = 4 if int(act_dtype) == 0 else 2
     for d in self._descs(descs, n_inputs):
       width, col = int(d["width"]), int(d["dst_col"])
       if vec4:
@@ -253,23 +273,57 @@ class DryOps:
         view = torch.as_strided(out, (ns, width), (dst_stride, 1), col)
         if int(d["flags"]) & 1:  # row slices: only samples with an id inside the shard store
           keep = hits > 0
+          if int(d["flags"]) & 6:  # ... plus ids outside the whole table (zero rows), one-hot
+            assert int(d["hotness"]) == 1
+            low = (ids < 0) if int(d["flags"]) & 2 else torch.zeros_like(ok)
+            high = (ids >= int(d["sub_rows"])) if int(d["flags"]) & 4 else torch.zeros_like(ok)
+            keep = keep | low | high
           view[keep] = pooled[keep].to(odt)
         else:
           view.copy_(pooled.to(odt))
 
-  def lookup_fwd_bulk(self, descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src_ptrs,
-                      dst_ptrs, rot, ids64, out_bf16):
-    """TMA bulk-copy variant: same contract, restricted to one-hot rows of <= 128 columns whose
-    16-byte pieces are aligned (what the engine must have checked before choosing it)."""
-    for d in self._descs(descs, n_inputs):
-      assert int(d["hotness"]) == 1 and not int(d["offsets"]) and not int(d["flags"])
-      assert int(d["width"]) % 4 == 0 and int(d["width"]) <= 128 and int(d["dst_col"]) % 4 == 0
-      assert int(d["table"]) % 16 == 0 and dst_stride % 4 == 0
-    self.lookup_fwd(descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src_ptrs, dst_ptrs,
-                    rot, ids64, out_bf16, True)
-    self.calls["lookup_fwd_bulk"] = self.calls.get("lookup_fwd_bulk", 0) + 1
-
   # -- index exchange ------------------------------------------------------------------------
+  def push_segments(self, segs, src, dst_ptrs, max_seg, sync):
+    """Index push: segment {dst rank, src offset, dst offset, n} of the local staging buffer is
+    stored into the id buffer of its owner."""
+    self._count("push_segments")
+    self._wait(sync)
+    esz = src.element_size()
+    flat = src.view(-1)
+    for r, so, do, n in segs.tolist():
+      assert n <= max_seg
+      dst = self.world.tensor(int(dst_ptrs[r]) + do * esz, src.dtype, n, "id push destination")
+      dst.copy_(flat[so:so + n])
+
+  def push_grad(self, routes, n_routes, src, dst_dtype, scale, sync):
+    """Gradient push: every route piece of the local gradient rows goes to its owner."""
+    self._count("push_grad")
+    self._wait(sync)
+    R = np.frombuffer(routes.numpy().tobytes(), dtype=GRAD_ROUTE)[:int(n_routes)]
+    ddt = self._ADT[int(dst_dtype)]
+    dsz = 4 if int(dst_dtype) == 0 else 2
+    rows = src.shape[0]
+    covered = torch.zeros(src.shape[1], dtype=torch.int32)
+    for r in R:
+      w, sc, dc, stride = int(r["width"]), int(r["src_col"]), int(r["dst_col"]), int(r["dst_stride"])
+      assert sc + w <= src.shape[1], "route piece outside the gradient row"
+      covered[sc:sc + w] += 1
+      last = (rows - 1) * stride + dc + w
+      self.world.check(int(r["dst"]), last * dsz, "gradient push destination")
+      out = self.world.tensor(int(r["dst"]), ddt, last, "gradient push destination")
+      torch.as_strided(out, (rows, w), (stride, 1), dc).copy_(
+          (src[:, sc:sc + w].float() * scale).to(ddt))
+
+  def rowslice_reduce(self, partial, out_ptr, out_stride, out_dtype, cols):
+    self._count("rowslice_reduce")
+    odt = self._ADT[int(out_dtype)]
+    world, rows, _ = partial.shape
+    red = partial.sum(dim=0)
+    for sc, dc, w in cols.tolist():
+      last = (rows - 1) * out_stride + dc + w
+      out = self.world.tensor(int(out_ptr), odt, last, "row-slice destination")
+      torch.as_strided(out, (rows, w), (out_stride, 1), dc).copy_(red[:, sc:sc + w].to(odt))
+
   def gather_segments(self, segs, src_ptrs, dst, max_seg):
     self._count("gather_segments")
     esz = dst.element_size()
@@ -298,24 +352,25 @@ class DryOps:
         goff[g_off + s * b + 1:g_off + (s + 1) * b + 1] = sp[1:] + pos
         pos += n
 
-  def copy_cast_2d(self, src, dst_ptr, dst_stride, dst_bf16, scale):
+  def copy_cast_2d(self, src, dst_ptr, dst_stride, dst_dtype, scale):
     self._count("copy_cast_2d")
     rows, cols = src.shape
-    ddt = torch.bfloat16 if dst_bf16 else torch.float32
+    ddt = self._ADT[int(dst_dtype)]
     out = self.world.tensor(int(dst_ptr), ddt, (rows - 1) * dst_stride + cols, "grad buffer")
     torch.as_strided(out, (rows, cols), (dst_stride, 1)).copy_((src.float() * scale).to(ddt))
 
   # -- backward ------------------------------------------------------------------------------
-  def _grad_rows(self, d, dd, ns, grad_ptrs, grad_stride, grad_bf16) -> torch.Tensor:
-    gdt = torch.bfloat16 if grad_bf16 else torch.float32
+  def _grad_rows(self, d, dd, ns, grad_ptrs, grad_stride, act_dtype) -> torch.Tensor:
+    gdt = self._ADT[int(act_dtype)]
     width, col = int(d["width"]), int(d["dst_col"])
     last = (ns - 1) * grad_stride + col + width
     g = self.world.tensor(int(grad_ptrs[dd]), gdt, last, "gradient source")
     return torch.as_strided(g, (ns, width), (grad_stride, 1), col).float()
 
   def scatter_add_bwd(self, descs, n_inputs, batch, src_batch, grad_batch, grad_stride, src_ptrs,
-                      grad_ptrs, rot, scale, scale_ptr, ids64, grad_bf16, vec4, vec8):
+                      grad_ptrs, rot, scale, scale_ptr, ids64, act_dtype, vec4, vec8, sync):
     self._count("scatter_add_bwd")
+    self._wait(sync)
     if scale_ptr:
       scale = scale * float(self.world.tensor(int(scale_ptr), torch.float32, 1, "lr")[0])
     for d in self._descs(descs, n_inputs):
@@ -325,21 +380,12 @@ class DryOps:
         vals, lens = self._ids_of(d, g0, g1, ids64, src_ptrs, src_batch)
         ids = vals + int(d["id_shift"])
         ok = (ids >= 0) & (ids < int(d["sub_rows"]))
-        g = self._grad_rows(d, dd, g1 - g0, grad_ptrs, grad_stride, grad_bf16)
+        g = self._grad_rows(d, dd, g1 - g0, grad_ptrs, grad_stride, act_dtype)
         w = torch.full((g1 - g0,), float(scale))
         if int(d["combiner"]) == 1:
           w = w / lens.clamp(min=1).to(w.dtype)
         per_id = (g * w.unsqueeze(1))[self._pool_index(lens)]
         table.index_add_(0, int(d["row_base"]) + ids[ok], per_id[ok])
-
-  def tiny_scatter_add_bwd(self, descs, n_inputs, batch, src_batch, grad_batch, grad_stride,
-                           src_ptrs, grad_ptrs, scale, scale_ptr, ids64, grad_bf16, max_rows,
-                           max_width):
-    for d in self._descs(descs, n_inputs):
-      assert int(d["sub_rows"]) <= max_rows and int(d["width"]) <= max_width
-      assert int(d["hotness"]) == 1 and not int(d["offsets"])
-    self.scatter_add_bwd(descs, n_inputs, batch, src_batch, grad_batch, grad_stride, src_ptrs,
-                         grad_ptrs, 0, scale, scale_ptr, ids64, grad_bf16, True, False)
 
   def sort_items(self, descs, tables, n_tables, n_inputs, batch, src_batch, src_ptrs, ids64,
                  n_items, total_rows, prefill_sentinel):
@@ -379,16 +425,20 @@ class DryOps:
 
   def segment_update(self, descs, tables, n_tables, batch, grad_batch, grad_stride, grad_ptrs,
                      keys, items, seg, n_unique, kind, lr, eps, beta1, beta2, bias1, bias2,
-                     grad_scale, weight_decay, lr_ptr, emit_keys, emit_rows, max_width, grad_bf16,
-                     vec4, scratch):
+                     grad_scale, weight_decay, lr_ptr, emit_keys, emit_rows, max_width, act_dtype,
+                     vec4, scratch, step_ptr):
     self._count("segment_update")
+    if step_ptr and kind == 3:
+      t = float(self.world.tensor(int(step_ptr), torch.float32, 1, "adam step")[0])
+      bias1, bias2 = 1.0 - beta1**t, 1.0 - beta2**t
     D = self._descs(descs, 1 << 30)
     T = self._descs(tables, n_tables, TABLE_DESC)
     if lr_ptr:
       lr = float(self.world.tensor(int(lr_ptr), torch.float32, 1, "lr")[0])
     sentinel = int(T[-1]["key_base"]) + int(T[-1]["rows"])
     bases = [int(t["key_base"]) for t in T]
-    gdt = torch.bfloat16 if grad_bf16 else torch.float32
+    gdt = self._ADT[int(act_dtype)]
+    gsz = 4 if int(act_dtype) == 0 else 2
     nu = int(n_unique[0])
     for u in range(nu):
       k0, k1 = int(seg[u]), int(seg[u + 1])
@@ -414,8 +464,8 @@ class DryOps:
             w = 1.0 / float(int(o[1]) - int(o[0]))
           else:
             w = 1.0 / float(int(d["hotness"]))
-        src = self.world.tensor(int(grad_ptrs[dd]) + (i * grad_stride + int(d["dst_col"])) *
-                                (2 if grad_bf16 else 4), gdt, width, "gradient source")
+        src = self.world.tensor(int(grad_ptrs[dd]) + (i * grad_stride + int(d["dst_col"])) * gsz,
+                                gdt, width, "gradient source")
         acc += w * src.float()
       g = acc * grad_scale
       if kind == 4:

@@ -1,23 +1,33 @@
 """Fused execution engine of :class:`DistributedEmbedding` (CUDA, sm_100a).
 
-Data flow of one training step on every rank (``W`` ranks, local batch ``b``, global ``B = W*b``):
+Data flow of one training step on every rank (``W`` ranks, local batch ``b``, global ``B = W*b``).
+Every exchange is a *push* over NVLink from inside a data kernel, and the cross-GPU ordering is
+folded into those kernels (head waits / tail signals on peer-mapped flag words, ``SyncArgs`` in
+``ops/csrc/de_b200.h``) - there is no separate barrier launch and no NCCL call on the hot path.
 
 forward
-  1. ids of all features are staged in a *symmetric* buffer ``in_buf`` (data loaders can write it
-     directly, so the H2D copy is the staging);
-  2. flag barrier; one pull kernel copies the ids of this rank's features out of every peer's
-     ``in_buf`` over NVLink (index all-to-all without NCCL);
-  3. one descriptor-driven lookup kernel gathers + pools the rows of *all* local tables and stores
-     every pooled row straight into the requester's ``out_buf`` at its final column offset
-     (pooled-vector all-to-all + reorder + column-slice concat fused into the gather epilogue);
-  4. flag barrier; ``out_buf`` is the ``[b, sum(widths)]`` activation (``concat=True`` returns it
-     without a copy).
+  1. ids of all features are staged in ``in_flat`` (data loaders can write it directly, so the
+     H2D copy is the staging);
+  2. ``push_segments``: every rank stores the id segments of each feature straight into the id
+     buffer of the rank that owns the feature (index all-to-all, reference DMP:211); its tail
+     signals "ids ready";
+  3. one descriptor-driven lookup kernel waits for the ids of all requesters, gathers + pools the
+     rows of *all* local tables and stores every pooled row into the requester's ``out_buf`` at
+     its final column offset (pooled-vector all-to-all + reorder + column-slice concat fused into
+     the gather epilogue); its tail signals "output ready";
+  4. the consumer of ``out_buf`` waits for that signal (a one-block kernel here, the head of the
+     interaction kernel in the hand-scheduled DLRM step).
 backward
-  1. the incoming gradient is written to the symmetric ``grad_buf``; flag barrier;
-  2. the owner pulls gradient rows from the peers' ``grad_buf`` inside the update kernel: either
-     vector ``red.global.add`` straight into the table (SGD), or the sorted / deduplicated path
-     that sums each unique row once and applies SGD / Adagrad / row-wise Adagrad / Adam in place.
-     No sparse gradient tensor, no host sync, no NCCL.
+  1. the producer of the gradient (``push_grad`` here, the interaction backward in the DLRM step)
+     stores every piece of its gradient rows into the *owner's* receive buffer
+     (``[B, sum(local widths)]``) and signals "gradient ready";
+  2. the owner's update kernel waits for all requesters, reads the gradient rows from local
+     memory and updates the tables in place: vector ``red.global.add`` (SGD), or the sorted /
+     deduplicated path that sums each unique row once and applies SGD / Adagrad / row-wise
+     Adagrad / Adam.  Its tail signals "consumed" so the next step's id push may overwrite.
+
+Ragged (variable hotness) inputs keep the pull-style index exchange (the global CSR needs every
+source's nnz): flag barrier + ``gather_segments`` / ``gather_ragged``.
 
 Replaces ``_call_table_parallel`` / ``_call_row_slice`` / ``_call_data_parallel`` plus Horovod's
 alltoall and the TF sparse optimizer kernels (reference dist_model_parallel.py:836-904).
@@ -25,20 +35,26 @@ alltoall and the TF sparse optimizer kernels (reference dist_model_parallel.py:8
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from ..ops import _native
-from ..ops._native import INPUT_DESC, TABLE_DESC
+from ..ops._native import DTYPE_CODE, GRAD_ROUTE, INPUT_DESC, TABLE_DESC
 from ..ops.ragged import RaggedIds
 from ..utils import nvtx
-from .comm import CommContext
+from .comm import CH_BARRIER0, CH_CONSUMED, CH_GRAD, CH_IDS, CH_OUT, CommContext
 
 _OPT_KIND = {"sgd": _native.OPT_SGD, "adagrad": _native.OPT_ADAGRAD,
              "rowwise_adagrad": _native.OPT_ROWWISE_ADAGRAD, "adam": _native.OPT_ADAM}
 _COMB = {None: 0, "sum": 0, "mean": 1}
+
+# InputDesc.flags
+FLAG_SKIP_EMPTY = 1   # store only when an id of the sample falls inside this shard
+FLAG_CATCH_LOW = 2    # with SKIP_EMPTY: also store (zeros) when the shifted id is negative
+FLAG_CATCH_HIGH = 4   # with SKIP_EMPTY: also store (zeros) when the shifted id >= sub_rows
 
 
 def _weight(layer):
@@ -61,12 +77,27 @@ class _FusedFn(torch.autograd.Function):
   def forward(ctx, engine, token, *weights):  # pylint: disable=arguments-differ
     ctx.engine = engine
     ctx.n_weights = len(weights)
+    ctx.done = False
+    engine._gen += 1
+    ctx.gen = engine._gen
     out = engine._run_forward()
+    # the backward of this call reads the engine's id / gradient buffers: remember the node so
+    # that a second forward before this backward is routed elsewhere (see FusedEngine.busy)
+    engine._pending = weakref.ref(ctx)
+    if not getattr(engine.de, "zero_copy_output", False):
+      out = out.clone()  # the engine buffer is overwritten by the next forward
     return out
 
   @staticmethod
   def backward(ctx, grad_out):  # pylint: disable=arguments-differ
-    grads = ctx.engine._run_backward(grad_out)
+    engine = ctx.engine
+    if ctx.gen != engine._gen:
+      raise RuntimeError(
+          "DistributedEmbedding (fused back end): another forward ran on this layer before the "
+          "backward of an earlier one; its index buffers were overwritten.  Call backward first, "
+          "or use backend='torch' for several forwards per backward.")
+    ctx.done = True
+    grads = engine._run_backward(grad_out)
     return (None, None) + tuple(grads)
 
 
@@ -97,13 +128,20 @@ class FusedEngine:
       self.out_cols.append(self.out_cols[-1] + w)
     self.total_width = self.out_cols[-1]
     self.compute_dtype = de.compute_dtype
-    if self.compute_dtype not in (torch.float32, torch.bfloat16):
-      raise ValueError("fused back end supports fp32 and bf16 activations")
+    if self.compute_dtype not in DTYPE_CODE:
+      raise ValueError("fused back end supports fp32, bf16 and fp16 activations")
+    self.act = DTYPE_CODE[self.compute_dtype]  # dtype code of activations / gradients on the wire
     self._key = None
+    self._gen = 0          # forward generation (see _FusedFn)
+    self._pending = None   # weakref to the autograd node of the last forward
     self._token = torch.zeros((), device=self.device)
     self.lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)
+    # Adam step count, device resident so that a captured CUDA graph keeps advancing it
+    self.step_t = torch.zeros(1, dtype=torch.float32, device=self.device)
     self.opt_state: Dict[int, List[torch.Tensor]] = {}
     self._tables_dirty = True
+    self._dp_targets = None
+    self._dp_target_desc = None
     # local model-parallel tables: table-parallel first, then row slices
     self.mp_layers = list(de.local_embedding_layers) + list(de.row_layers)
     self.n_col_tables = len(de.local_embedding_layers)
@@ -113,10 +151,22 @@ class FusedEngine:
   def _ptr(self, t: torch.Tensor) -> int:
     return t.data_ptr() if self.dry else _dev_ptr(t)
 
+  def _sync(self, wait: int = -1, wait_abs: int = -1, signal: int = -1):
+    return self.ctx.sync(wait=wait, wait_abs=wait_abs, signal=signal) if self.W > 1 else []
+
   # ------------------------------------------------------------------ capabilities
+  def busy(self) -> bool:
+    """True while a forward that recorded an autograd graph has not run its backward (and the
+    graph is still alive): the engine's id / output / gradient buffers belong to that call, so a
+    further forward must not run on the engine (the caller falls back to the torch back end;
+    the reference layer can be called any number of times)."""
+    node = self._pending() if self._pending is not None else None
+    return node is not None and not node.done
+
   def supports(self, inputs) -> bool:
     st, de = self.st, self.de
     col_inputs = set(st.input_groups[1]) if de.dp_input else set(range(len(inputs)))
+    imap = st.input_table_map
     for i, x in enumerate(inputs):
       if isinstance(x, RaggedIds):
         if i not in col_inputs:  # ragged only for table-parallel features
@@ -124,7 +174,47 @@ class FusedEngine:
         continue
       if not isinstance(x, torch.Tensor) or x.dim() > 2:
         return False
+      if x.dim() == 2 and x.shape[1] != 1:
+        # the kernels always pool a sample's ids: a table without a combiner keeps them apart
+        # ([b, h, width]) -> torch back end for every group (table parallel, replicated, row)
+        t = imap[i] if de.dp_input else \
+            st.table_groups[1][st.map_groups[1][st.input_ids_list[self.rank][i]]]
+        if st.global_configs[t].get("combiner") is None:
+          return False
     return True
+
+  # ------------------------------------------------------------------ plan -> layouts
+  def _mp_layout(self, r: int, hots: Optional[Tuple[int, ...]], B: int):
+    """Owner-side layout of rank ``r``: item offsets of its local inputs in the id buffer
+    (needs the hotness of every input: dp_input mode, or ``r`` = this rank) and their column
+    offsets / widths in its gradient receive buffer.  Every rank computes every rank's layout
+    from the global plan."""
+    de, st = self.de, self.st
+    col_group = st.input_groups[1]
+    col_map = st.map_groups[1]
+    my_inputs = st.input_ids_list[r] if st.table_groups[1] else []
+    items, cols, widths, pos, col = [], [], [], 0, 0
+    for li, k in enumerate(my_inputs):
+      shard = next(s for s in st.shards[r] if s.table == col_map[k])
+      if hots is not None:
+        gi = col_group[k] if de.dp_input else li
+        items.append(pos)
+        pos += B * abs(hots[gi])
+      cols.append(col)
+      widths.append(int(shard.width))
+      col += int(shard.width)
+    row_inputs = st.input_groups[2] if de.dp_input else []
+    for j, gi in enumerate(row_inputs):
+      m = st.map_groups[2][j]
+      w = int(st.row_sliced_configs[r][m]["output_dim"])
+      if hots is not None:
+        items.append(pos)
+        pos += B * abs(hots[gi])
+      cols.append(col)
+      widths.append(w)
+      col += w
+    return {"items": items, "n_items": pos, "cols": cols, "widths": widths, "width": col,
+            "n_col": len(my_inputs)}
 
   # ------------------------------------------------------------------ plan -> descriptors
   def _build(self, b: int, hots: Tuple[int, ...], ids64: bool):
@@ -135,7 +225,7 @@ class FusedEngine:
     B = b * W if de.dp_input else b
     lb = b if de.dp_input else b // W  # local (requester) batch
     self.B, self.lb, self.hots, self.ids64, self.id_dtype = B, lb, hots, ids64, id_dtype
-    csz = 2 if self.compute_dtype == torch.bfloat16 else 4
+    csz = 4 if self.act == 0 else 2
 
     col_group = st.input_groups[1] if de.dp_input else list(range(len(hots)))
     col_map = st.map_groups[1]
@@ -148,13 +238,16 @@ class FusedEngine:
     for i, r in enumerate(self.ragged):
       if r:
         rag_index[i] = len(rag_index)
+    # index exchange: "push" (fire-and-forget stores into the owners' id buffers, signalling
+    # folded into the kernels) unless a ragged input needs the pull-style global CSR build
+    self.id_mode = "none" if W == 1 or not de.dp_input else ("pull" if self.any_ragged else "push")
     if de.dp_input:
       in_off, pos = [], 0
       for h in hots:
         in_off.append(pos)
         pos += b * abs(h)
       self.in_elems = max(pos, 1)
-      if W > 1:
+      if self.id_mode == "pull":
         self.in_buf = self.ctx.alloc(self.in_elems * idsz, "ids_in")
         in_flat = self.in_buf.view(id_dtype, (self.in_elems,))
         self.in_ptrs = self.in_buf.peer_ptrs()
@@ -182,22 +275,28 @@ class FusedEngine:
       self.in_buf, self.in_flat, self.in_views, self.in_ptrs = None, None, None, []
       self.split_views = {}
 
-    # --- model-parallel id buffer (global batch of every local input)
+    # --- owner-side layouts of every rank (id buffer items, gradient receive columns)
+    layouts = [self._mp_layout(r, hots if (de.dp_input or r == rank) else None, B)
+               for r in range(W)]
+    mine = layouts[rank]
     my_inputs = st.input_ids_list[rank] if st.table_groups[1] else []
-    col_items, pos = [], 0
-    for li, k in enumerate(my_inputs):
-      gi = col_group[k] if de.dp_input else li
-      h = abs(hots[gi])
-      col_items.append(pos)
-      pos += B * h
-    row_items = []
     row_inputs = st.input_groups[2] if de.dp_input else []
-    for gi in row_inputs:
-      row_items.append(pos)
-      pos += B * abs(hots[gi])
-    self.n_items = pos
+    n_col, n_row = len(my_inputs), len(row_inputs)
+    col_items, row_items = mine["items"][:n_col], mine["items"][n_col:]
+    self.n_items = mine["n_items"]
+    self.recv_width = max(mine["width"], 1)
     need_copy = (W > 1) or (not de.dp_input)
-    self.ids_mp = torch.zeros(max(pos, 1), dtype=id_dtype, device=dev) if need_copy else None
+    # model-parallel id buffer (global batch of every local input); peers store into it
+    if self.id_mode == "push":
+      n_sym = max(max(l["n_items"] for l in layouts), 1)
+      self.ids_buf = self.ctx.alloc(n_sym * idsz, "ids_mp")
+      self.ids_mp = self.ids_buf.view(id_dtype, (n_sym,))
+      self.ids_ptrs = self.ids_buf.peer_ptrs()
+    else:
+      self.ids_buf = None
+      self.ids_mp = torch.zeros(max(self.n_items, 1), dtype=id_dtype, device=dev) \
+          if need_copy else None
+      self.ids_ptrs = []
     # global-batch CSR offsets of the ragged local inputs ([B + 1] each)
     my_ragged = [li for li, k in enumerate(my_inputs)
                  if self.ragged[col_group[k] if de.dp_input else li]]
@@ -223,27 +322,34 @@ class FusedEngine:
     self.tdesc_np = tdesc
     self.max_width = max([int(_weight(l).shape[1]) for l in self.mp_layers] + [1])
 
-    # --- output layout
+    # --- output buffer (requester side) and gradient receive buffer (owner side)
     tw = self.total_width
     out_bytes = max(lb * tw * csz, 16)
+    recv_w_sym = max(max(l["width"] for l in layouts), 1)
     if W > 1:
       self.out_buf = self.ctx.alloc(out_bytes, "emb_out")
-      self.grad_buf = self.ctx.alloc(out_bytes, "emb_grad")
       self.out = self.out_buf.view(self.compute_dtype, (lb, tw))
-      self.grad = self.grad_buf.view(self.compute_dtype, (lb, tw))
       self.out_ptrs = self.out_buf.peer_ptrs()
-      self.grad_ptrs = self.grad_buf.peer_ptrs()
+      self.recv_buf = self.ctx.alloc(max(B * recv_w_sym * csz, 16), "emb_grad_recv")
+      self.recv = self.recv_buf.view(self.compute_dtype, (B, self.recv_width))
+      recv_ptrs = self.recv_buf.peer_ptrs()
     else:
-      self.out_buf = self.grad_buf = None
+      self.out_buf = self.recv_buf = None
       self.out = torch.zeros(lb, tw, dtype=self.compute_dtype, device=dev)
-      self.grad = torch.zeros(lb, tw, dtype=self.compute_dtype, device=dev)
       self.out_ptrs = [self.out.data_ptr()]
-      self.grad_ptrs = [self.grad.data_ptr()]
+      self.recv = torch.zeros(B, self.recv_width, dtype=self.compute_dtype, device=dev)
+      recv_ptrs = [self.recv.data_ptr()]
+    self.recv_ptr = [self.recv.data_ptr()]
+    # requester-layout gradient of the replicated inputs (written by a fused producer such as
+    # the DLRM interaction backward; the generic path reads the incoming gradient directly)
+    dp_inputs = st.input_groups[0] if de.dp_input else []
+    self.grad = torch.zeros(lb, tw, dtype=self.compute_dtype, device=dev) if len(dp_inputs) \
+        else None
 
     # --- table-parallel descriptors
     pieces = {(p.rank, p.local_input): p for p in st.output_pieces}
-    cdesc = np.zeros(len(my_inputs), dtype=INPUT_DESC)
-    segs, rsegs = [], []
+    cdesc = np.zeros(n_col, dtype=INPUT_DESC)
+    segs, rsegs = [], []      # pull mode: what this rank fetches
     for li, k in enumerate(my_inputs):
       gi = col_group[k] if de.dp_input else li
       t_in_group = col_map[k]
@@ -270,7 +376,7 @@ class FusedEngine:
       d["item_off"] = col_items[li]
       if layer.combiner is None and hots[gi] != 1:
         raise ValueError("table-parallel lookups without a combiner need one id per sample")
-      if de.dp_input and W > 1:
+      if self.id_mode == "pull":
         if self.ragged[gi]:
           rsegs.append([in_off[gi], col_items[li], rag_index[gi] * (b + 1),
                         goff_index[li] * (B + 1)])
@@ -279,10 +385,14 @@ class FusedEngine:
             segs.append([s, in_off[gi], col_items[li] + s * b * hots[gi], b * hots[gi]])
     self.cdesc_np = cdesc
 
-    # --- row-slice descriptors (partial pools land in rs_buf[d][slot = my rank])
-    rdesc = np.zeros(len(row_inputs), dtype=INPUT_DESC)
+    # --- row-slice descriptors.  One-hot inputs: exactly one rank owns a sample's id, it stores
+    # the row straight into the requester's output (rank 0 / the last rank also catch ids below /
+    # above the table and store zeros).  Multi-hot inputs: every rank stores its partial pool
+    # into slot `rank` of the requester's partial buffer, the requester sums the W slots.
+    rdesc = np.zeros(n_row, dtype=INPUT_DESC)
     self.rs_width = 0
-    self.rs_cols = []
+    self.rs_cols = []     # multi-hot row inputs: (gi, partial col, width)
+    self.row_onehot = []
     for j, gi in enumerate(row_inputs):
       m = st.map_groups[2][j]
       layer = de.row_layers[m]
@@ -294,25 +404,38 @@ class FusedEngine:
       d["sub_rows"] = w.shape[0]
       d["width"] = w.shape[1]
       d["hotness"] = hots[gi]
-      d["dst_col"] = self.rs_width
       d["combiner"] = _COMB[layer.combiner]
       d["local_table"] = self.n_col_tables + m
       d["item_off"] = row_items[j]
-      d["flags"] = 1
-      self.rs_cols.append((gi, self.rs_width, int(w.shape[1])))
-      self.rs_width += int(w.shape[1])
-      for s in range(W):
-        segs.append([s, in_off[gi], row_items[j] + s * b * hots[gi], b * hots[gi]])
+      onehot = hots[gi] == 1
+      self.row_onehot.append(onehot)
+      if onehot:
+        d["dst_col"] = self.out_cols[gi]
+        d["flags"] = FLAG_SKIP_EMPTY | (FLAG_CATCH_LOW if rank == 0 else 0) | \
+            (FLAG_CATCH_HIGH if rank == W - 1 else 0)
+      else:
+        d["dst_col"] = self.rs_width
+        d["flags"] = 0
+        self.rs_cols.append((gi, self.rs_width, int(w.shape[1])))
+        self.rs_width += int(w.shape[1])
+      if self.id_mode == "pull":
+        for s in range(W):
+          segs.append([s, in_off[gi], row_items[j] + s * b * hots[gi], b * hots[gi]])
     self.rdesc_np = rdesc
-    if len(row_inputs):
+    oh = np.array(self.row_onehot, dtype=bool) if n_row else np.zeros(0, dtype=bool)
+    # forward launches: [table-parallel + one-hot row inputs] -> out_buf; multi-hot rows -> rs_buf
+    self.fwd_main_np = np.concatenate([cdesc, rdesc[oh]]) if n_row else cdesc
+    self.fwd_rs_np = rdesc[~oh] if n_row else rdesc
+    if len(self.fwd_rs_np):
       self.rs_buf = self.ctx.alloc(W * lb * self.rs_width * 4, "row_slice_partials")
       self.rs = self.rs_buf.view(torch.float32, (W, lb, self.rs_width))
       self.rs_ptrs = self.rs_buf.peer_ptrs(rank * lb * self.rs_width * 4)
+      self.rs_cols_t = torch.tensor([[c0, self.out_cols[gi], w] for gi, c0, w in self.rs_cols],
+                                    dtype=torch.int32, device=dev)
     else:
       self.rs_buf = None
 
     # --- replicated tables: plain local lookup of the local batch
-    dp_inputs = st.input_groups[0] if de.dp_input else []
     ddesc = np.zeros(len(dp_inputs), dtype=INPUT_DESC)
     for j, gi in enumerate(dp_inputs):
       m = st.map_groups[0][j]
@@ -328,6 +451,64 @@ class FusedEngine:
       d["combiner"] = _COMB[layer.combiner]
       d["local_table"] = m
     self.ddesc_np = ddesc
+    # persistent dense-gradient buffers of the replicated tables (generic autograd path)
+    self._dp_grad_flat, self._dp_grad_views, self._dp_grad_desc = None, [], None
+    self._dp_grad_desc_np = None
+    if len(de.dp_layers):
+      offs, pos = [], 0
+      for layer in de.dp_layers:
+        offs.append(pos)
+        pos += (_weight(layer).numel() + 3) // 4 * 4
+      self._dp_grad_flat = torch.zeros(max(pos, 4), dtype=torch.float32, device=dev)
+      self._dp_grad_views = [self._dp_grad_flat[o:o + _weight(l).numel()].view(_weight(l).shape)
+                             for o, l in zip(offs, de.dp_layers)]
+      dd = ddesc.copy()
+      for j in range(len(dd)):
+        dd[j]["table"] = self._dp_grad_views[int(dd[j]["local_table"])].data_ptr()
+      self._dp_grad_desc_np = dd
+
+    # --- index push: what this rank sends ({dst rank, src offset, dst offset, n} per segment)
+    push = []
+    if self.id_mode == "push":
+      for r in range(W):
+        L = layouts[r]
+        r_inputs = st.input_ids_list[r] if st.table_groups[1] else []
+        for li, k in enumerate(r_inputs):
+          gi = col_group[k]
+          n = b * hots[gi]
+          push.append([r, in_off[gi], L["items"][li] + rank * n, n])
+        for j, gi in enumerate(row_inputs):
+          n = b * hots[gi]
+          push.append([r, in_off[gi], L["items"][L["n_col"] + j] + rank * n, n])
+    self.push_segs = torch.tensor(push, dtype=torch.int64, device=dev) if push else None
+    self.max_push = max([s[3] for s in push]) if push else 0
+
+    # --- gradient routes: where every piece of this requester's gradient row goes
+    routes = []
+    for r in range(W):
+      L = layouts[r]
+      base = recv_ptrs[r] + rank * lb * L["width"] * csz
+      r_inputs = st.input_ids_list[r] if st.table_groups[1] else []
+      for li, k in enumerate(r_inputs):
+        p = pieces[(r, li)]
+        gi_global = st.input_groups[1][k]
+        routes.append((self.out_cols[gi_global] + p.col_offset, L["widths"][li], base, L["width"],
+                       L["cols"][li]))
+      for j, gi in enumerate(row_inputs):
+        routes.append((self.out_cols[gi], L["widths"][L["n_col"] + j], base, L["width"],
+                       L["cols"][L["n_col"] + j]))
+    dp_routes = [(self.out_cols[gi], self.out_widths[gi], self.grad.data_ptr(), tw,
+                  self.out_cols[gi]) for gi in dp_inputs]
+
+    def pack(rs):
+      rs = sorted(rs, key=lambda x: (x[0], x[2]))
+      arr = np.zeros(len(rs), dtype=GRAD_ROUTE)
+      for i, (src_col, width, dst, stride, dst_col) in enumerate(rs):
+        arr[i]["dst"], arr[i]["dst_stride"] = dst, stride
+        arr[i]["src_col"], arr[i]["width"], arr[i]["dst_col"] = src_col, width, dst_col
+      return arr
+    self.routes_mp_np = pack(routes)
+    self.routes_all_np = pack(routes + dp_routes)
 
     self.segs = torch.tensor(segs, dtype=torch.int64, device=dev) if segs else None
     self.max_seg = max([s[3] for s in segs]) if segs else 0
@@ -335,28 +516,22 @@ class FusedEngine:
     self.max_rcap = b * max([abs(h) for h, r in zip(hots, self.ragged) if r] + [0])
     self.my_ragged_mp = my_ragged if not de.dp_input else []
     self.col_items = col_items
+    # backward descriptors of all model-parallel inputs: gradient columns of the receive buffer
+    mp = np.concatenate([cdesc, rdesc]) if n_row else cdesc.copy()
+    for i in range(len(mp)):
+      mp[i]["dst_col"] = mine["cols"][i]
+    self.mpdesc_np = mp
+    self.n_mp_inputs = len(mp)
+
     widths = [int(x) for x in list(cdesc["width"]) + list(rdesc["width"]) + list(ddesc["width"])]
-    cols = [int(x) for x in list(cdesc["dst_col"]) + list(ddesc["dst_col"])]
+    cols = [int(x) for x in list(self.fwd_main_np["dst_col"]) + list(self.fwd_rs_np["dst_col"]) +
+            list(ddesc["dst_col"]) + list(mp["dst_col"])]
     self.vec4 = all(w % 4 == 0 for w in widths) and all(c % 4 == 0 for c in cols) and \
-        tw % 4 == 0 and self.rs_width % 4 == 0
-    # 16-byte gradient pulls (8 columns per lane).  Faster in isolation (151 -> 109 us at 8 GPUs)
-    # but the whole step regressed at 4 and 8 GPUs in a same-box A/B (0.995 -> 1.11 ms at N=4), so
-    # it is opt-in until that interaction is understood: DE_B200_VEC8_PULL=1.
-    self.vec8 = os.environ.get("DE_B200_VEC8_PULL", "0") == "1" and self.vec4 and \
-        all(w % 8 == 0 for w in widths) and all(c % 8 == 0 for c in cols) and tw % 8 == 0 and \
-        not len(row_inputs)
-    # shared-memory pre-reduction of tiny one-hot tables in the SGD backward (experimental)
-    self.tiny_tables = os.environ.get("DE_B200_TINY_TABLES", "0") == "1"
-    # TMA bulk row copies for one-hot table-parallel / replicated lookups (experimental):
-    # every input one id per sample, rows of at most 128 fp32 columns, 16-byte aligned pieces
-    def bulk_ok(desc):
-      return len(desc) > 0 and bool(np.all(desc["hotness"] == 1)) and \
-          bool(np.all(desc["offsets"] == 0)) and bool(np.all(desc["width"] % 4 == 0)) and \
-          bool(np.all(desc["width"] <= 128)) and bool(np.all(desc["dst_col"] % 4 == 0)) and \
-          bool(np.all(desc["flags"] == 0))
-    bulk = os.environ.get("DE_B200_LOOKUP_BULK", "0") == "1" and tw % 4 == 0
-    self.bulk_c = bulk and bulk_ok(cdesc)
-    self.bulk_d = bulk and bulk_ok(ddesc)
+        tw % 4 == 0 and self.rs_width % 4 == 0 and self.recv_width % 4 == 0
+    # 16-byte gradient loads (8 columns per lane) in the SGD update: DE_B200_VEC8_GRAD=1
+    self.vec8 = os.environ.get("DE_B200_VEC8_GRAD", "0") == "1" and self.vec4 and \
+        all(w % 8 == 0 for w in widths) and all(c % 8 == 0 for c in cols) and \
+        self.recv_width % 8 == 0
     self._upload()
     self._key = (b, hots, ids64)
 
@@ -364,14 +539,15 @@ class FusedEngine:
     """(Re)upload descriptor arrays; table pointers / optimizer state may have changed."""
     dev = self.device
     up = _native.upload_struct_array
-    self.cdesc = up(self.cdesc_np, dev) if len(self.cdesc_np) else None
-    self.rdesc = up(self.rdesc_np, dev) if len(self.rdesc_np) else None
+    self.fwd_main = up(self.fwd_main_np, dev) if len(self.fwd_main_np) else None
+    self.fwd_rs = up(self.fwd_rs_np, dev) if len(self.fwd_rs_np) else None
     self.ddesc = up(self.ddesc_np, dev) if len(self.ddesc_np) else None
+    self.mpdesc = up(self.mpdesc_np, dev) if len(self.mpdesc_np) else None
+    self.routes_mp = up(self.routes_mp_np, dev) if len(self.routes_mp_np) else None
+    self.routes_all = up(self.routes_all_np, dev) if len(self.routes_all_np) else None
+    if self._dp_grad_desc_np is not None and len(self.ddesc_np):
+      self._dp_grad_desc = up(self._dp_grad_desc_np, dev)
     self._refresh_tables()
-    # one descriptor array for the backward of all model-parallel inputs
-    mp = np.concatenate([self.cdesc_np, self.rdesc_np]) if len(self.rdesc_np) else self.cdesc_np
-    self.mpdesc = up(mp, dev) if len(mp) else None
-    self.n_mp_inputs = len(mp)
 
   def _refresh_tables(self):
     opt = self.de._fused_optimizer
@@ -393,6 +569,8 @@ class FusedEngine:
     if opt is None:
       return
     kind = opt["kind"]
+    self.step_t.fill_(float(opt.get("step", 0)))
+
     def like(w, value, shape=None):
       t = torch.full(shape or tuple(w.shape), value, dtype=torch.float32, device=w.device)
       # state of offloaded tables stays on the host (pinned, read zero-copy by the kernels)
@@ -411,9 +589,15 @@ class FusedEngine:
   def update_lr(self, lr: float):
     self.lr_t.fill_(lr)
 
+  def step_count(self) -> int:
+    """Optimizer steps applied so far (device counter: survives CUDA-graph replays)."""
+    return int(round(float(self.step_t.item())))
+
   def optimizer_state_dict(self) -> Dict[str, Any]:
+    """Local (sharding dependent) optimizer state; see
+    :meth:`DistributedEmbedding.get_optimizer_state` for the global, resharding-safe layout."""
     return {"state": {m: [s.detach().cpu() for s in st] for m, st in self.opt_state.items()},
-            "step": (self.de._fused_optimizer or {}).get("step", 0)}
+            "step": self.step_count()}
 
   def load_optimizer_state_dict(self, state):
     if not self.opt_state:
@@ -421,8 +605,10 @@ class FusedEngine:
     for m, tensors in state.get("state", {}).items():
       for dst, src in zip(self.opt_state[int(m)], tensors):
         dst.copy_(src)
+    step = int(state.get("step", 0))
+    self.step_t.fill_(float(step))
     if self.de._fused_optimizer is not None:
-      self.de._fused_optimizer["step"] = state.get("step", 0)
+      self.de._fused_optimizer["step"] = step
 
   # ------------------------------------------------------------------ forward
   def prepare(self, local_batch: int, hotness: Sequence[int], ids64: bool = False):
@@ -509,75 +695,98 @@ class FusedEngine:
 
   def _run_forward(self):
     with nvtx.range("emb_forward"):
-      return self._run_forward_impl()
+      self.launch_forward()
+      self.wait_output()
+      return self.out
 
-  def _run_forward_impl(self):
+  @property
+  def has_mp(self) -> bool:
+    return self.fwd_main is not None or self.fwd_rs is not None
+
+  @property
+  def out_needs_reduce(self) -> bool:
+    """Multi-hot row-sliced inputs: the requester still has to sum the owners' partial pools
+    (``wait_output`` does it); a fused consumer can only fold the wait when this is False."""
+    return self.rs_buf is not None
+
+  def launch_forward(self):
+    """Index exchange + lookups.  The pooled rows of this rank's tables are on their way to the
+    requesters when this returns; the *consumer* of ``self.out`` must wait for the owners'
+    "output ready" signals (:meth:`wait_output`, or ``sync_out_wait()`` folded into its kernel)."""
     ops, W, rank = self.ops, self.W, self.rank
     B, lb = self.B, self.lb
-    bf16 = self.compute_dtype == torch.bfloat16
-    if self.rs_buf is not None:
-      self.rs.zero_()
-    if W > 1:
-      self.ctx.barrier(0)  # every rank's ids are staged (and its partial buffer is cleared)
-      if self.segs is not None:
-        ops.gather_segments(self.segs, self.in_ptrs, self.ids_mp, self.max_seg)
-      if self.rsegs is not None:
-        ops.gather_ragged(self.rsegs, self.in_ptrs, self.split_ptrs, self.ids_mp, self.goff,
-                          self.lb, self.max_rcap)
+    wait_ids = -1
+    if W > 1 and self.has_mp:
+      if self.id_mode == "push":
+        # head: every owner has consumed last step's ids; tail: my ids are in the owners' buffers
+        ops.push_segments(self.push_segs, self.in_flat, self.ids_ptrs, self.max_push,
+                          self._sync(wait_abs=CH_CONSUMED, signal=CH_IDS))
+        wait_ids = CH_IDS
+      elif self.id_mode == "pull":
+        self.ctx.barrier(CH_BARRIER0)  # every rank's ids are staged
+        if self.segs is not None:
+          ops.gather_segments(self.segs, self.in_ptrs, self.ids_mp, self.max_seg)
+        if self.rsegs is not None:
+          ops.gather_ragged(self.rsegs, self.in_ptrs, self.split_ptrs, self.ids_mp, self.goff,
+                            self.lb, self.max_rcap)
+      else:  # model-parallel inputs: nothing to exchange, but the output buffers of the
+        # requesters may only be overwritten once they are done with the previous step
+        ops.sync_only(self._sync(signal=CH_IDS))
+        wait_ids = CH_IDS
     if self.ddesc is not None:
-      if self.bulk_d:
-        ops.lookup_fwd_bulk(self.ddesc, len(self.ddesc_np), lb, lb, lb, self.total_width, [],
-                            [self.out.data_ptr()], 0, self.ids64, bf16)
-      else:
-        ops.lookup_fwd(self.ddesc, len(self.ddesc_np), lb, lb, lb, self.total_width, [],
-                       [self.out.data_ptr()], 0, self.ids64, bf16, self.vec4)
-    if self.cdesc is not None:
-      if self.bulk_c:
-        ops.lookup_fwd_bulk(self.cdesc, len(self.cdesc_np), B, B, lb, self.total_width, [],
-                            self.out_ptrs, rank, self.ids64, bf16)
-      else:
-        ops.lookup_fwd(self.cdesc, len(self.cdesc_np), B, B, lb, self.total_width, [],
-                       self.out_ptrs, rank, self.ids64, bf16, self.vec4)
-    if self.rdesc is not None:
-      ops.lookup_fwd(self.rdesc, len(self.rdesc_np), B, B, lb, self.rs_width, [], self.rs_ptrs,
-                     rank, self.ids64, False, self.vec4)
-    if W > 1:
-      self.ctx.barrier(1)  # all pooled rows have landed in my out_buf
+      ops.lookup_fwd(self.ddesc, len(self.ddesc_np), lb, lb, lb, self.total_width, [],
+                     [self.out.data_ptr()], 0, self.ids64, self.act, self.vec4, [])
+    if self.fwd_main is not None:
+      sig = CH_OUT if self.fwd_rs is None else -1
+      ops.lookup_fwd(self.fwd_main, len(self.fwd_main_np), B, B, lb, self.total_width, [],
+                     self.out_ptrs, rank, self.ids64, self.act, self.vec4,
+                     self._sync(wait=wait_ids, signal=sig))
+      wait_ids = -1  # later launches of this stream are ordered behind the wait
+    if self.fwd_rs is not None:
+      ops.lookup_fwd(self.fwd_rs, len(self.fwd_rs_np), B, B, lb, self.rs_width, [], self.rs_ptrs,
+                     rank, self.ids64, 0, self.vec4, self._sync(wait=wait_ids, signal=CH_OUT))
+
+  def sync_out_wait(self):
+    """``sync`` spec that makes a consumer kernel wait for the owners' "output ready" signals."""
+    return self._sync(wait=CH_OUT) if (self.W > 1 and self.has_mp) else []
+
+  def wait_output(self):
+    """Consumer side of the forward: wait until every owner's rows have landed in ``self.out``
+    and sum the partial pools of multi-hot row-sliced inputs."""
+    if self.W > 1 and self.has_mp:
+      self.ops.sync_only(self._sync(wait=CH_OUT))
     if self.rs_buf is not None:
-      red = self.rs.sum(dim=0)
-      for gi, c0, w in self.rs_cols:
-        self.out[:, self.out_cols[gi]:self.out_cols[gi] + w] = red[:, c0:c0 + w]
-    return self.out
+      self.ops.rowslice_reduce(self.rs, self.out.data_ptr(), self.total_width, self.act,
+                               self.rs_cols_t)
 
   # ------------------------------------------------------------------ backward
   def _run_backward(self, grad_out: torch.Tensor):
-    ops, W, rank, de = self.ops, self.W, self.rank, self.de
-    B, lb = self.B, self.lb
-    bf16 = self.compute_dtype == torch.bfloat16
-    if grad_out.data_ptr() != self.grad.data_ptr():
-      if grad_out.dtype not in (torch.float32, torch.bfloat16) or grad_out.stride(-1) != 1:
-        grad_out = grad_out.float().contiguous()
-      ops.copy_cast_2d(grad_out, self.grad.data_ptr(), self.total_width, bf16, 1.0)
-    if W > 1:
-      self.ctx.barrier(2)  # every rank's gradient buffer is complete
+    ops, de = self.ops, self.de
+    lb = self.lb
+    if grad_out.dtype not in DTYPE_CODE or grad_out.stride(-1) != 1:
+      grad_out = grad_out.float().contiguous()
+    self._grad_out_live = grad_out if self.dry else None  # addressable for the plan interpreter
+    # gradient all-to-all: every piece of my rows goes straight into its owner's receive buffer
+    if self.routes_mp is not None:
+      ops.push_grad(self.routes_mp, len(self.routes_mp_np), grad_out, self.act, 1.0,
+                    self._sync(signal=CH_GRAD))
     grads: List[Optional[torch.Tensor]] = []
-    # replicated tables: dense local gradients (all-reduced later with the MLP gradients)
-    for m, layer in enumerate(de.dp_layers):
-      w = _weight(layer)
-      if not w.requires_grad:
-        grads.append(None)
-        continue
-      g = torch.zeros_like(w)
-      self._dp_grad_live = g  # keeps the buffer addressable for the plan interpreter (dry_run.py)
-      sel = [j for j in range(len(self.ddesc_np)) if int(self.ddesc_np[j]["local_table"]) == m]
-      d = self.ddesc_np[sel].copy()
-      d["table"] = g.data_ptr()
-      dd = _native.upload_struct_array(d, self.device)
-      ops.scatter_add_bwd(dd, len(d), lb, lb, lb, self.total_width, [], [self.grad.data_ptr()], 0,
-                          1.0, 0, self.ids64, bf16, self.vec4, False)
-      grads.append(g)
-    grads += self._backward_mp(bf16)
+    # replicated tables: dense local gradients (all-reduced later with the MLP gradients), read
+    # straight from the incoming gradient; persistent buffers + descriptors, one launch
+    if len(de.dp_layers):
+      need = [_weight(l).requires_grad for l in de.dp_layers]
+      if any(need) and self._dp_grad_desc is not None:
+        self._dp_grad_flat.zero_()
+        ops.scatter_add_bwd(self._dp_grad_desc, len(self.ddesc_np), lb, lb, lb,
+                            grad_out.stride(0), [], [grad_out.data_ptr()], 0, 1.0, 0, self.ids64,
+                            DTYPE_CODE[grad_out.dtype], self._grad_vec4(grad_out), False, [])
+      for m in range(len(de.dp_layers)):
+        grads.append(self._dp_grad_views[m].clone() if need[m] else None)
+    grads += self._backward_mp()
     return grads
+
+  def _grad_vec4(self, g: torch.Tensor) -> bool:
+    return self.vec4 and g.stride(0) % 4 == 0 and g.data_ptr() % 16 == 0
 
   def set_dp_grad_targets(self, targets: Optional[Sequence[torch.Tensor]]):
     """Persistent dense-gradient buffers of the replicated tables, one fp32 ``[rows, width]``
@@ -595,8 +804,9 @@ class FusedEngine:
     self._dp_targets = targets
     self._dp_target_desc = None
 
-  def _scatter_dp_grads(self, bf16: bool):
-    """Local-batch gradient of every replicated table into its persistent target (one launch)."""
+  def _scatter_dp_grads(self):
+    """Local-batch gradient of every replicated table into its persistent target (one launch);
+    the gradient rows come from ``self.grad`` (requester layout, written by a fused producer)."""
     if not len(self.ddesc_np):
       return
     key = (self._key, tuple(t.data_ptr() for t in self._dp_targets))
@@ -607,77 +817,76 @@ class FusedEngine:
       self._dp_target_desc = (key, _native.upload_struct_array(d, self.device), len(d))
     _, dd, n = self._dp_target_desc
     self.ops.scatter_add_bwd(dd, n, self.lb, self.lb, self.lb, self.total_width, [],
-                             [self.grad.data_ptr()], 0, 1.0, 0, self.ids64, bf16, self.vec4, False)
+                             [self.grad.data_ptr()], 0, 1.0, 0, self.ids64, self.act, self.vec4,
+                             False, [])
+
+  def sync_grad_signal(self):
+    """``sync`` spec for a fused gradient producer (it stores through ``routes_all`` and
+    signals "gradient ready" from its tail)."""
+    return self._sync(signal=CH_GRAD) if (self.W > 1 and self.mpdesc is not None) else []
 
   def backward_inplace(self):
-    """Backward when the gradient was already written into ``self.grad`` (e.g. by the fused
-    interaction-backward kernel): barrier + fused table update; replicated tables accumulate
-    their dense gradient into the targets given to :meth:`set_dp_grad_targets`."""
-    bf16 = self.compute_dtype == torch.bfloat16
-    if self.W > 1:
-      self.ctx.barrier(2)
+    """Backward when a fused producer (e.g. the DLRM interaction backward) already pushed the
+    gradient through ``routes_all`` and signalled: fused table update; replicated tables
+    accumulate their dense gradient into the targets given to :meth:`set_dp_grad_targets`."""
     if len(self.de.dp_layers):
       if getattr(self, "_dp_targets", None) is None:
         raise RuntimeError("backward_inplace needs set_dp_grad_targets() for replicated tables")
-      self._scatter_dp_grads(bf16)
-    self._backward_mp(bf16)
+      self._scatter_dp_grads()
+    self._backward_mp()
 
-  def _backward_mp(self, bf16: bool) -> List[Optional[torch.Tensor]]:
+  def _backward_mp(self) -> List[Optional[torch.Tensor]]:
     with nvtx.range("emb_backward_update"):
-      return self._backward_mp_impl(bf16)
+      return self._backward_mp_impl()
 
-  def _backward_mp_impl(self, bf16: bool) -> List[Optional[torch.Tensor]]:
+  def _backward_mp_impl(self) -> List[Optional[torch.Tensor]]:
     ops, de = self.ops, self.de
     n_mp = len(self.mp_layers)
-    if self.mpdesc is None or not any(_weight(l).requires_grad for l in self.mp_layers):
+    if self.mpdesc is None:
+      return [None] * n_mp
+    multi = self.W > 1
+    if not any(_weight(l).requires_grad for l in self.mp_layers):
+      if multi:  # keep the signalling protocol in step: consume the gradient signal
+        ops.sync_only(self._sync(wait=CH_GRAD, signal=CH_CONSUMED))
       return [None] * n_mp
     opt = de._fused_optimizer
     if opt is not None and opt["kind"] != "sgd" and not self.opt_state:
       self.reset_optimizer_state()
     if self._tables_dirty:
       self._refresh_tables()
-    B, lb = self.B, self.lb
-    # row-slice partial gradients: the gradient of an input lives in grad_buf at the input's
-    # output columns for *both* groups, but row descriptors carry rs_buf columns -> patch once
+    B = self.B
     if opt is not None and opt["kind"] == "sgd" and not opt.get("deterministic", False) and \
         not self.has_offload:
-      if self.tiny_tables and self.vec4:
-        # experimental: one-hot inputs of tables with <= 64 rows are pre-reduced in shared memory
-        main, n_main, tiny, n_tiny, t_rows, t_width = self._bwd_desc_split()
-        if n_main:
-          ops.scatter_add_bwd(main, n_main, B, B, lb, self.total_width, [], self.grad_ptrs,
-                              self.rank, -de.mp_grad_scale, self.lr_t.data_ptr(), self.ids64,
-                              bf16, self.vec4, self.vec8 and self.W > 1)
-        if n_tiny:
-          ops.tiny_scatter_add_bwd(tiny, n_tiny, B, B, lb, self.total_width, [], self.grad_ptrs,
-                                   -de.mp_grad_scale, self.lr_t.data_ptr(), self.ids64, bf16,
-                                   t_rows, t_width)
-        return [None] * n_mp
-      ops.scatter_add_bwd(self._bwd_desc(), self.n_mp_inputs, B, B, lb, self.total_width, [],
-                          self.grad_ptrs, self.rank, -de.mp_grad_scale, self.lr_t.data_ptr(),
-                          self.ids64, bf16, self.vec4, self.vec8 and self.W > 1)
+      # head: every requester's gradient rows have landed; tail: ids + gradients are consumed
+      ops.scatter_add_bwd(self.mpdesc, self.n_mp_inputs, B, B, B, self.recv_width, [],
+                          self.recv_ptr, 0, -de.mp_grad_scale, self.lr_t.data_ptr(), self.ids64,
+                          self.act, self.vec4, self.vec8,
+                          self._sync(wait=CH_GRAD, signal=CH_CONSUMED))
       return [None] * n_mp
-    keys, items, seg, n_unique = ops.sort_items(self._bwd_desc(), self.tdesc, n_mp,
-                                                self.n_mp_inputs, B, B, [], self.ids64,
-                                                self.n_items, self.total_rows, self.any_ragged)
+    if multi:
+      ops.sync_only(self._sync(wait=CH_GRAD))
+    keys, items, seg, n_unique = ops.sort_items(self.mpdesc, self.tdesc, n_mp, self.n_mp_inputs,
+                                                B, B, [], self.ids64, self.n_items,
+                                                self.total_rows, self.any_ragged)
     if opt is not None:
-      opt["step"] += 1
-      t = opt["step"]
-      bias1 = 1.0 - opt["beta1"]**t
-      bias2 = 1.0 - opt["beta2"]**t
-      ops.segment_update(self._bwd_desc(), self.tdesc, n_mp, B, lb, self.total_width,
-                         self.grad_ptrs, keys, items, seg, n_unique, _OPT_KIND[opt["kind"]],
-                         opt["lr"], opt["eps"], opt["beta1"], opt["beta2"], bias1, bias2,
-                         de.mp_grad_scale, opt["weight_decay"], self.lr_t.data_ptr(), None, None,
-                         self.max_width, bf16, self.vec4, self._balanced_scratch())
+      self.step_t.add_(1.0)  # device counter: bias corrections stay right under graph replay
+      ops.segment_update(self.mpdesc, self.tdesc, n_mp, B, B, self.recv_width, self.recv_ptr,
+                         keys, items, seg, n_unique, _OPT_KIND[opt["kind"]], opt["lr"],
+                         opt["eps"], opt["beta1"], opt["beta2"], 1.0, 1.0, de.mp_grad_scale,
+                         opt["weight_decay"], self.lr_t.data_ptr(), None, None, self.max_width,
+                         self.act, self.vec4, self._balanced_scratch(), self.step_t.data_ptr())
+      if multi:
+        ops.sync_only(self._sync(signal=CH_CONSUMED))
       return [None] * n_mp
     # no fused optimizer: materialise deduplicated sparse gradients (reference semantics)
     emit_keys = torch.empty(self.n_items, dtype=torch.int64, device=self.device)
     emit_rows = torch.empty(self.n_items, self.max_width, dtype=torch.float32, device=self.device)
-    ops.segment_update(self._bwd_desc(), self.tdesc, n_mp, B, lb, self.total_width, self.grad_ptrs,
-                       keys, items, seg, n_unique, _native.OPT_EMIT, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0,
-                       de.mp_grad_scale, 0.0, 0, emit_keys, emit_rows, self.max_width, bf16,
-                       self.vec4, None)
+    ops.segment_update(self.mpdesc, self.tdesc, n_mp, B, B, self.recv_width, self.recv_ptr, keys,
+                       items, seg, n_unique, _native.OPT_EMIT, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0,
+                       de.mp_grad_scale, 0.0, 0, emit_keys, emit_rows, self.max_width, self.act,
+                       self.vec4, None, 0)
+    if multi:
+      ops.sync_only(self._sync(signal=CH_CONSUMED))
     nu = int(n_unique.item())
     emit_keys, emit_rows = emit_keys[:nu], emit_rows[:nu]
     bases = [int(x) for x in self.tdesc_np["key_base"]] + [self.total_rows]
@@ -708,36 +917,3 @@ class FusedEngine:
     if cur is None or cur.numel() < need:
       self._scratch = torch.zeros(need, dtype=torch.float32, device=self.device)
     return self._scratch
-
-  def _bwd_desc_split(self):
-    """(main descs, n, tiny descs, n, max tiny rows, max tiny width): the backward descriptors
-    split into inputs served by the RED scatter kernel and one-hot inputs of tiny tables."""
-    if getattr(self, "_split_cache", None) is not None and self._split_key == self._key:
-      return self._split_cache
-    self._bwd_desc()
-    mp = self._bwd_desc_np
-    tiny = (mp["hotness"] == 1) & (mp["offsets"] == 0) & (mp["sub_rows"] <= 64) & \
-        (mp["width"] % 4 == 0) & (mp["sub_rows"] * mp["width"] * 4 <= 96 * 1024)
-    main_np, tiny_np = mp[~tiny], mp[tiny]
-    main = _native.upload_struct_array(main_np, self.device) if len(main_np) else None
-    tin = _native.upload_struct_array(tiny_np, self.device) if len(tiny_np) else None
-    t_rows = int(tiny_np["sub_rows"].max()) if len(tiny_np) else 0
-    t_width = int(tiny_np["width"].max()) if len(tiny_np) else 0
-    self._split_cache = (main, len(main_np), tin, len(tiny_np), t_rows, t_width)
-    self._split_key = self._key
-    return self._split_cache
-
-  def _bwd_desc(self):
-    """Backward descriptors: same as forward but row-slice inputs read their gradient at the
-    input's final output columns of grad_buf."""
-    if getattr(self, "_bwd_desc_cache", None) is not None and self._bwd_key == self._key:
-      return self._bwd_desc_cache
-    mp = np.concatenate([self.cdesc_np, self.rdesc_np]) if len(self.rdesc_np) else \
-        self.cdesc_np.copy()
-    n_c = len(self.cdesc_np)
-    for j, (gi, _, _) in enumerate(self.rs_cols):
-      mp[n_c + j]["dst_col"] = self.out_cols[gi]
-    self._bwd_desc_np = mp
-    self._bwd_desc_cache = _native.upload_struct_array(mp, self.device)
-    self._bwd_key = self._key
-    return self._bwd_desc_cache

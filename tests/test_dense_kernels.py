@@ -25,7 +25,7 @@ def test_interaction_fwd_bwd(n_emb, dim):
   n_out = (n_emb + 1) * n_emb // 2 + dim
   zw = (n_out + 7) // 8 * 8
   z = torch.full((b, zw), 7.0, device="cuda", dtype=torch.bfloat16)
-  ops.interact_fwd(bottom, emb, n_emb, z)
+  ops.interact_fwd(bottom, emb, n_emb, z, [])
   bf = bottom.float().requires_grad_(True)
   ef = emb.float().requires_grad_(True)
   ref = ref_interact(bf, ef, n_emb)
@@ -35,9 +35,74 @@ def test_interaction_fwd_bwd(n_emb, dim):
   ref.backward(dz[:, :n_out].float())
   dbottom = torch.empty(b, dim, device="cuda", dtype=torch.bfloat16)
   demb = torch.empty(b, n_emb * dim + 16, device="cuda", dtype=torch.bfloat16)
-  ops.interact_bwd(bottom, emb, n_emb, dz, dbottom, demb.data_ptr(), demb.stride(0), 1.0)
+  ops.interact_bwd(bottom, emb, n_emb, dz, dbottom, demb.data_ptr(), demb.stride(0), 1.0, None, 0,
+                   [])
   torch.testing.assert_close(dbottom.float(), bf.grad, rtol=3e-2, atol=3e-2)
   torch.testing.assert_close(demb[:, :n_emb * dim].float(), ef.grad, rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("n_emb,dim,b", [(26, 128, 5003), (7, 64, 9001), (3, 128, 4099),
+                                         (26, 128, 37)])
+def test_interaction_bwd_double_buffered(n_emb, dim, b):
+  """Batches with several samples per warp exercise the cp.async double buffer and the in-place
+  shared-memory epilogue of the default interaction backward."""
+  ops = _native.require()
+  torch.manual_seed(1)
+  bottom = (torch.randn(b, dim, device="cuda") * 0.5).bfloat16()
+  emb = (torch.randn(b, n_emb * dim, device="cuda") * 0.5).bfloat16()
+  n_out = (n_emb + 1) * n_emb // 2 + dim
+  zw = (n_out + 7) // 8 * 8
+  bf = bottom.float().requires_grad_(True)
+  ef = emb.float().requires_grad_(True)
+  ref = ref_interact(bf, ef, n_emb)
+  dz = (torch.randn(b, zw, device="cuda") * 0.1).bfloat16()
+  ref.backward(dz[:, :n_out].float())
+  dbottom = torch.empty(b, dim, device="cuda", dtype=torch.bfloat16)
+  demb = torch.empty(b, n_emb * dim + 16, device="cuda", dtype=torch.bfloat16)
+  ops.interact_bwd(bottom, emb, n_emb, dz, dbottom, demb.data_ptr(), demb.stride(0), 1.0, None, 0,
+                   [])
+  torch.cuda.synchronize()
+  torch.testing.assert_close(dbottom.float(), bf.grad, rtol=3e-2, atol=3e-2)
+  torch.testing.assert_close(demb[:, :n_emb * dim].float(), ef.grad, rtol=3e-2, atol=3e-2)
+
+
+def test_interaction_bwd_routed():
+  """Gradient pieces routed to separate destination buffers (what the distributed step does
+  with the owners' receive buffers): column slices of a feature, permuted features, and a
+  destination row stride different from the source."""
+  import numpy as np
+  from distributed_embeddings_b200.ops._native import GRAD_ROUTE, upload_struct_array
+  ops = _native.require()
+  torch.manual_seed(2)
+  n_emb, dim, b = 5, 128, 3001
+  bottom = (torch.randn(b, dim, device="cuda") * 0.5).bfloat16()
+  emb = (torch.randn(b, n_emb * dim, device="cuda") * 0.5).bfloat16()
+  n_out = (n_emb + 1) * n_emb // 2 + dim
+  zw = (n_out + 7) // 8 * 8
+  bf = bottom.float().requires_grad_(True)
+  ef = emb.float().requires_grad_(True)
+  ref = ref_interact(bf, ef, n_emb)
+  dz = (torch.randn(b, zw, device="cuda") * 0.1).bfloat16()
+  ref.backward(dz[:, :n_out].float())
+  # "owner" A gets features 4, 0 and the upper half of feature 2; owner B the rest
+  a = torch.zeros(b, 2 * 128 + 64 + 8, device="cuda", dtype=torch.bfloat16)
+  bb = torch.zeros(b, 2 * 128 + 64, device="cuda", dtype=torch.bfloat16)
+  pieces = [  # (src_col, width, dst, dst_col)
+      (4 * 128, 128, a, 0), (0, 128, a, 128), (2 * 128 + 64, 64, a, 256),
+      (1 * 128, 128, bb, 64), (2 * 128, 64, bb, 0), (3 * 128, 128, bb, 192)]
+  routes = np.zeros(len(pieces), dtype=GRAD_ROUTE)
+  for i, (sc, w, dst, dc) in enumerate(sorted(pieces)):
+    routes[i]["dst"], routes[i]["dst_stride"] = dst.data_ptr(), dst.stride(0)
+    routes[i]["src_col"], routes[i]["width"], routes[i]["dst_col"] = sc, w, dc
+  dbottom = torch.empty(b, dim, device="cuda", dtype=torch.bfloat16)
+  ops.interact_bwd(bottom, emb, n_emb, dz, dbottom, 0, 0, 0.5, upload_struct_array(routes, "cuda"),
+                   len(pieces), [])
+  torch.cuda.synchronize()
+  torch.testing.assert_close(dbottom.float(), bf.grad, rtol=3e-2, atol=3e-2)
+  for sc, w, dst, dc in pieces:
+    torch.testing.assert_close(dst[:, dc:dc + w].float(), 0.5 * ef.grad[:, sc:sc + w],
+                               rtol=3e-2, atol=3e-2)
+  assert torch.count_nonzero(a[:, 320:]) == 0
 
 
 @pytest.mark.parametrize("cols", [128, 256, 512, 1024])
@@ -102,43 +167,3 @@ def test_dense_sgd_and_cast_pad():
   ops.cast_pad(src, dst)
   torch.testing.assert_close(dst[:, :13].float(), src.bfloat16().float())
   assert torch.count_nonzero(dst[:, 13:]) == 0
-
-
-@pytest.mark.skipif(__import__("os").environ.get("DE_B200_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="double-buffered interaction backward (DE_B200_INTERACT_V2=1) not yet "
-                    "validated on hardware; set DE_B200_TEST_EXPERIMENTAL=1")
-def test_interaction_bwd_v2_subprocess():
-  """The env switch is read once per process: run the comparison in a child with a batch large
-  enough (several samples per warp) to exercise the double buffer."""
-  import os
-  import subprocess
-  import sys
-  code = r'''
-import torch
-from distributed_embeddings_b200.ops import _native
-from tests.test_dense_kernels import ref_interact
-ops = _native.require()
-for n_emb, dim, b in [(26, 128, 5003), (7, 64, 9001), (3, 128, 4099), (26, 128, 37)]:
-  torch.manual_seed(1)
-  bottom = (torch.randn(b, dim, device="cuda") * 0.5).bfloat16()
-  emb = (torch.randn(b, n_emb * dim, device="cuda") * 0.5).bfloat16()
-  n_out = (n_emb + 1) * n_emb // 2 + dim
-  zw = (n_out + 7) // 8 * 8
-  bf = bottom.float().requires_grad_(True)
-  ef = emb.float().requires_grad_(True)
-  ref = ref_interact(bf, ef, n_emb)
-  dz = (torch.randn(b, zw, device="cuda") * 0.1).bfloat16()
-  ref.backward(dz[:, :n_out].float())
-  dbottom = torch.empty(b, dim, device="cuda", dtype=torch.bfloat16)
-  demb = torch.empty(b, n_emb * dim + 16, device="cuda", dtype=torch.bfloat16)
-  ops.interact_bwd(bottom, emb, n_emb, dz, dbottom, demb.data_ptr(), demb.stride(0), 1.0)
-  torch.cuda.synchronize()
-  torch.testing.assert_close(dbottom.float(), bf.grad, rtol=3e-2, atol=3e-2)
-  torch.testing.assert_close(demb[:, :n_emb * dim].float(), ef.grad, rtol=3e-2, atol=3e-2)
-print("V2_OK")
-'''
-  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-  env = dict(os.environ, DE_B200_INTERACT_V2="1", PYTHONPATH=root)
-  out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True,
-                       text=True, timeout=600, check=False)
-  assert out.returncode == 0 and "V2_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

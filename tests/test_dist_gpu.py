@@ -69,13 +69,7 @@ def test_dlrm_fast_world2(optimizer):
   launch("case_dlrm_fast_step", world=2, device_type="cuda", backend="fused", optimizer=optimizer)
 
 
-_EXPERIMENTAL = __import__("os").environ.get("DE_B200_TEST_EXPERIMENTAL", "0") == "1"
-
-
 @pytest.mark.gpu
-@pytest.mark.skipif(not _EXPERIMENTAL, reason="randomised plans on the fused back end: added after "
-                    "the round-1 GPU budget was spent (the CPU/gloo version runs in test_dist_cpu); "
-                    "set DE_B200_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("world", [1, 2, 4])
 def test_fuzz_plans_fused(world):
   if torch.cuda.device_count() < world:
@@ -86,8 +80,6 @@ def test_fuzz_plans_fused(world):
 
 @pytest.mark.gpu
 @pytest.mark.multigpu
-@pytest.mark.skipif(not _EXPERIMENTAL, reason="fused back end on process sub-groups: added after "
-                    "the round-1 GPU budget was spent; set DE_B200_TEST_EXPERIMENTAL=1")
 def test_subgroups_fused():
   if torch.cuda.device_count() < 4:
     pytest.skip("needs 4 GPUs")
@@ -96,23 +88,9 @@ def test_subgroups_fused():
 
 @pytest.mark.gpu
 @pytest.mark.multigpu
-@pytest.mark.skipif(not _EXPERIMENTAL, reason="replicated tables in the fast DLRM step: added "
-                    "after the round-1 GPU budget was spent; set DE_B200_TEST_EXPERIMENTAL=1")
 def test_dlrm_fast_world2_replicated_tables():
   # tables have 200..525 rows x 128: replicate those up to 300 rows
   launch("case_dlrm_fast_step", world=2, device_type="cuda", backend="fused", optimizer="sgd",
          dp_threshold=300 * 128)
 
 
-@pytest.mark.gpu
-@pytest.mark.skipif(not _EXPERIMENTAL, reason="TMA bulk-copy forward (DE_B200_LOOKUP_BULK=1): added "
-                    "after the round-1 GPU budget was spent; set DE_B200_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("world", [1, 2])
-@pytest.mark.parametrize("case", ["case_basic", "case_memory_balanced", "case_shared_dp",
-                                  "case_column_slice_threshold", "case_int32_ids",
-                                  "case_data_parallel", "case_fuzz"])
-def test_fused_bulk_lookup(case, world, monkeypatch):
-  if torch.cuda.device_count() < world:
-    pytest.skip(f"needs {world} GPUs")
-  monkeypatch.setenv("DE_B200_LOOKUP_BULK", "1")  # inherited by the spawned ranks
-  launch(case, world=world, device_type="cuda", backend="fused")

@@ -375,33 +375,8 @@ def test_multi_step_with_batch_size_change(world, kind):
 
 
 @pytest.mark.parametrize("world", [1, 2, 4])
-def test_tiny_table_split_path(world, monkeypatch):
-  """DE_B200_TINY_TABLES=1: one-hot inputs of tables with <= 64 rows go through the
-  shared-memory pre-reduction launch, everything else through the RED scatter; together they
-  must still produce the plain SGD update."""
-  monkeypatch.setenv("DE_B200_TINY_TABLES", "1")
-  seen = {"tiny": 0, "main": 0}
-  orig_tiny = dry_run.DryOps.tiny_scatter_add_bwd
-  orig_main = dry_run.DryOps.scatter_add_bwd
-
-  def tiny(self, *a, **k):
-    seen["tiny"] += 1
-    return orig_tiny(self, *a, **k)
-
-  def main(self, *a, **k):
-    seen["main"] += 1
-    return orig_main(self, *a, **k)
-
-  monkeypatch.setattr(dry_run.DryOps, "tiny_scatter_add_bwd", tiny)
-  monkeypatch.setattr(dry_run.DryOps, "scatter_add_bwd", main)
-  outcomes = [run_plan(8800 * world + s, world, "sgd") for s in range(8)]
-  assert outcomes.count("ok") >= 5, outcomes
-  assert seen["tiny"] > 0 and seen["main"] > seen["tiny"]  # tiny calls main once internally
-
-
-@pytest.mark.parametrize("world", [1, 2, 4])
 def test_backward_inplace_with_replicated_tables(world):
-  """The hand-scheduled step's path: gradient already in the engine's buffer, replicated tables
+  """The hand-scheduled step's path: gradient pushed by a fused producer, replicated tables
   accumulate their local-batch dense gradient into persistent targets (later all-reduced with
   the dense parameters), model-parallel tables are updated in place."""
   rng = np.random.default_rng(77 + world)
@@ -430,7 +405,12 @@ def test_backward_inplace_with_replicated_tables(world):
       out = de([torch.from_numpy(i[sl]) for i in ids], concat=True)
       exp = np.concatenate([tables[t][ids[t][sl]] for t in range(len(sizes))], 1)
       np.testing.assert_allclose(out.numpy(), exp, rtol=1e-5, atol=1e-5)
-      eng.grad.copy_(torch.from_numpy(np.concatenate([g[sl] for g in grads], 1)))
+      # what the fused producer (the DLRM interaction backward) does: every piece of the local
+      # gradient rows goes through `routes_all` to its owner (replicated inputs: to the local
+      # requester-layout buffer), "gradient ready" is signalled from the same launch
+      g = torch.from_numpy(np.concatenate([g[sl] for g in grads], 1))
+      eng.ops.push_grad(eng.routes_all, len(eng.routes_all_np), g, eng.act, 1.0,
+                        eng.sync_grad_signal())
       eng.backward_inplace()
 
   dry_run.run_ranks(sim, rank_fn)
@@ -503,29 +483,3 @@ def test_optimizer_state_checkpoint_resume(kind):
   sim_d, des_d = make(saved_w)
   step(sim_d, des_d, batches[1])
   assert any(not np.allclose(a, b, rtol=1e-5, atol=1e-6) for a, b in zip(straight, assemble(des_d)))
-
-
-@pytest.mark.parametrize("world", [1, 2, 4])
-def test_bulk_lookup_selection(world, monkeypatch):
-  """DE_B200_LOOKUP_BULK=1: the TMA bulk-copy forward is chosen only when every descriptor of a
-  launch qualifies (one id per sample, <= 128 aligned columns), and the plan still computes the
-  right thing through it."""
-  monkeypatch.setenv("DE_B200_LOOKUP_BULK", "1")
-  used = {"bulk": 0, "plain": 0}
-  orig = dry_run.build_engines
-  last = {}
-
-  def spy(embs, w, **kw):
-    sim, des = orig(embs, w, **kw)
-    last["des"] = des
-    return sim, des
-
-  monkeypatch.setattr(dry_run, "build_engines", spy)
-  for s in range(10):
-    if run_plan(6100 * world + s, world, "sgd") != "ok":
-      continue
-    for de in last["des"]:
-      c = de._engine.ops.calls
-      used["bulk"] += c.get("lookup_fwd_bulk", 0)
-      used["plain"] += c.get("lookup_fwd", 0) - c.get("lookup_fwd_bulk", 0)
-  assert used["bulk"] > 0 and used["plain"] > 0, used

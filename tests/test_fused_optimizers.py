@@ -82,47 +82,3 @@ def test_fused_optimizer_on_skewed_ids(kind, width, combiner):
     want = reference_update(kind, w0, state, [ids[i] for i in sel], [cols[i] for i in sel], lr,
                             eps, 0.1, 1.0, combiner, [hots[i] for i in sel])
     torch.testing.assert_close(torch.from_numpy(w_after[t]).to(dev), want, rtol=2e-4, atol=2e-4)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("DE_B200_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="tiny-table shared-memory scatter (DE_B200_TINY_TABLES=1) not yet "
-                    "validated on hardware; set DE_B200_TEST_EXPERIMENTAL=1")
-def test_tiny_table_sgd_subprocess():
-  """SGD update with tiny one-hot tables routed through the shared-memory pre-reduction kernel
-  vs a plain PyTorch scatter (the env switch is read when the engine is built: child process)."""
-  import os
-  import subprocess
-  import sys
-  code = r'''
-import torch
-from distributed_embeddings_b200 import DistributedEmbedding
-torch.manual_seed(0)
-dev = torch.device("cuda", 0)
-rows = [3, 10, 40, 64, 65, 1000, 5]
-widths = [128, 128, 32, 64, 128, 128, 16]
-b, lr = 5003, 0.5
-for dtype in (torch.float32, torch.bfloat16):
-  embs = [{"input_dim": r, "output_dim": w, "combiner": None} for r, w in zip(rows, widths)]
-  de = DistributedEmbedding(embs, device=dev, backend="fused", compute_dtype=dtype)
-  de.set_optimizer("sgd", lr=lr)
-  w0 = [torch.from_numpy(w).to(dev) for w in de.get_weights()]
-  ids = [torch.randint(0, r, (b,), device=dev, dtype=torch.int32) for r in rows]
-  out = de(ids, concat=True)
-  assert de._engine.tiny_tables
-  grad = (torch.randn(b, sum(widths), device=dev) * 0.1).to(dtype)
-  out.backward(grad)
-  torch.cuda.synchronize()
-  w1 = [torch.from_numpy(w).to(dev) for w in de.get_weights()]
-  col = 0
-  for t, (r, w) in enumerate(zip(rows, widths)):
-    exp = w0[t].clone()
-    exp.index_add_(0, ids[t].long(), -lr * grad[:, col:col + w].float())
-    col += w
-    torch.testing.assert_close(w1[t], exp, rtol=1e-3, atol=2e-3)
-print("TINY_OK")
-'''
-  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-  env = dict(os.environ, DE_B200_TINY_TABLES="1", PYTHONPATH=root)
-  out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True,
-                       text=True, timeout=600, check=False)
-  assert out.returncode == 0 and "TINY_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -60,9 +60,6 @@ def test_fused_dgrad_relu_bias(m, n, k):
   torch.testing.assert_close(colsum, ref.sum(0), rtol=2e-2, atol=0.5)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DE_B200_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="CTA-pair (cta_group::2) kernel not yet validated on hardware; "
-                    "set DE_B200_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("m,n,k", [(256, 256, 64), (512, 256, 128), (4096, 1024, 480),
                                    (8192, 1024, 1024), (777, 512, 512), (300, 256, 256)])
 @pytest.mark.parametrize("relu", [True, False])
