@@ -21,7 +21,8 @@ sanitize:
 	compute-sanitizer --tool racecheck $(PYTHON) -m pytest tests/test_dense_kernels.py -q -m gpu -x -k interaction
 
 sass:
-	cuobjdump -sass distributed_embeddings_b200/_C.so > profiles/sass_full.txt
+	$(PYTHON) tools/dump_sass.py
+	$(PYTHON) tools/sass_census.py > profiles/sass_census.txt
 
 bench:
 	$(PYTHON) bench.py --gpus 1 --steps 50 --warmup 10

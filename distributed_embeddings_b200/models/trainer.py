@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from ..parallel.comm import CommContext
-from ..parallel.hybrid import GradBucket
+from ..parallel.hybrid import GradBucket, SparseRowOptimizer
 from ..utils.lr_schedule import LearningRateScheduler
 
 
@@ -38,6 +38,11 @@ class HybridTrainer:
     self.emb = model.embedding
     self.emb.set_optimizer(embedding_optimizer, lr=lr, **(embedding_optimizer_kwargs or {}))
     self.dense_params: List[nn.Parameter] = list(model.dense_parameters())
+    # Lookups that do not run on the fused engine (torch / NCCL back end, or inputs the engine
+    # does not support) hand the model-parallel tables ordinary sparse autograd gradients:
+    # a row-sparse optimizer with the same math as the fused kernels applies them.
+    self.mp_opt = SparseRowOptimizer(self.emb.mp_parameters(), embedding_optimizer, lr=lr,
+                                     **(embedding_optimizer_kwargs or {}))
     self.scheduler = scheduler
     self.lr = lr
     dev = self.dense_params[0].device
@@ -69,6 +74,7 @@ class HybridTrainer:
     for g in self.opt.param_groups:
       g["lr"] = lr
     self.lr_t.fill_(float(lr))
+    self.mp_opt.set_lr(lr)
     self.emb.set_learning_rate(lr)
 
   def _dense_step(self):
@@ -128,4 +134,5 @@ class HybridTrainer:
     self.bucket.gather_grads_()
     self.bucket.allreduce_(average=True)
     self._dense_step()
+    self.mp_opt.step()  # no-op when the fused engine already updated the tables in backward
     return loss.detach()

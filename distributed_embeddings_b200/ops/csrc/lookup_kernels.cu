@@ -122,6 +122,15 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
     const IdReader<IdT> rd = make_reader<IdT>(D, src, src_batch);
     const bool onehot = (D.hotness == 1) && (D.offsets == nullptr);
     const bool skip_empty = (D.flags & 1) != 0;  // row slices: only the owner of an id writes
+    // one-hot: the 32 ids of the tile arrive with ONE coalesced load (lane = sample) and are
+    // handed to the lane groups by shuffle - the row gathers then issue back to back instead
+    // of each waiting for its own dependent id load
+    long long tile_id = -1;
+    if (onehot && lane < tc.nsamp) {
+      int n;
+      const IdT* p = rd.sample(tc.g0 + lane, n);
+      tile_id = static_cast<long long>(*p) + D.id_shift;
+    }
 
     for (int c0 = 0; c0 < nvec; c0 += lpr) {        // column pass (one pass when W <= 128)
       const int cv = c0 + li;
@@ -137,10 +146,8 @@ lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t bat
             const int r = r0 + u * rpw + sub;
             ok[u] = (r < tc.nsamp) && col_ok;
             acc[u].zero();
+            const int64_t id = __shfl_sync(0xffffffffu, tile_id, r & 31);
             if (ok[u]) {
-              int n;
-              const IdT* p = rd.sample(tc.g0 + r, n);
-              const int64_t id = static_cast<int64_t>(*p) + D.id_shift;
               if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows)) {
                 acc[u] = ld_f32<VEC>(table + (D.row_base + id) * W + col);
               } else if (skip_empty) {

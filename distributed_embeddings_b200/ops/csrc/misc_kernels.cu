@@ -83,6 +83,11 @@ __global__ void integer_lookup_kernel(int64_t* __restrict__ table, int64_t n_slo
                       static_cast<unsigned long long>(key));
         cur = static_cast<int64_t>(prev);
         if (cur == kEmptyKey) {  // slot claimed by this thread: allocate the index, publish it
+          // Threads that raced past the capacity check above may find the counter exhausted:
+          // their key is recorded as OOV (value 0).  That is the contract - once the vocabulary
+          // is full every new key is OOV for good (reference CU:445-464) - and it costs at most
+          // one slot per thread of the launch that crossed the limit (the table has 50 % slack
+          // and later launches stop inserting at the check above).
           const int64_t idx = static_cast<int64_t>(
               atomicAdd(reinterpret_cast<unsigned long long*>(next_index), 1ULL));
           value = idx < capacity ? idx : 0;
@@ -91,9 +96,14 @@ __global__ void integer_lookup_kernel(int64_t* __restrict__ table, int64_t n_slo
         }
       }
       if (cur == key) {  // present (maybe still being published by its owner)
-        int64_t v;
-        while ((v = ld_acquire_i64(kp + 1)) == kUnpublished) __nanosleep(32);
-        value = v;
+        // the owner is a few instructions away from its release store; like every other wait of
+        // this code base the spin is bounded (a lost publisher yields OOV, not a hung GPU)
+        int64_t v = ld_acquire_i64(kp + 1);
+        for (int spin = 0; v == kUnpublished && spin < (1 << 22); ++spin) {
+          __nanosleep(32);
+          v = ld_acquire_i64(kp + 1);
+        }
+        value = v == kUnpublished ? 0 : v;
         break;
       }
       slot = slot + 1 == n_slots ? 0 : slot + 1;

@@ -591,7 +591,8 @@ class DistributedEmbedding(nn.Module):
                   out: Optional[np.ndarray], col_start: int, chunk: int = 1 << 26):
     """Broadcast a [rows, width] shard from ``owner`` in row chunks; collectors copy it into
     ``out[:, col_start:col_start+width]``."""
-    dev = self._comm_device()
+    dev = self._comm_device() if getattr(self, "_bcast_hook", None) is None else \
+        torch.device("cpu")
     step = max(1, chunk // max(1, width))
     for r0 in range(0, rows, step):
       r1 = min(rows, r0 + step)
@@ -600,7 +601,11 @@ class DistributedEmbedding(nn.Module):
       else:
         buf = torch.empty(r1 - r0, width, dtype=torch.float32, device=dev)
       if self.world_size > 1:
-        dist.broadcast(buf, src=self._global_rank(owner), group=self.group)
+        hook = getattr(self, "_bcast_hook", None)  # plan interpreter: ranks are threads
+        if hook is not None:
+          buf = hook(buf, owner, self.rank)
+        else:
+          dist.broadcast(buf, src=self._global_rank(owner), group=self.group)
       if out is not None:
         out[r0:r1, col_start:col_start + width] = buf.cpu().numpy()
 
@@ -616,44 +621,62 @@ class DistributedEmbedding(nn.Module):
     loads on one GPU.  Only rank 0 receives the arrays unless ``all_ranks`` (other ranks get an
     empty list for the model-parallel tables they do not own).
     """
+    weights = self.weights
+    n_dp, n_col = len(self.dp_layers), len(self.local_embedding_layers)
+    return self._gather_global(weights[:n_dp], weights[n_dp:n_dp + n_col],
+                               weights[n_dp + n_col:], all_ranks)
+
+  def _gather_global(self, dp_tensors, col_tensors, row_tensors, all_ranks: bool,
+                     per_row: bool = False) -> List[Optional[np.ndarray]]:
+    """Assemble global per-table arrays from this rank's local tensors (one per replicated
+    layer / fused local table / row shard; ``None`` entries of ``dp_tensors`` are skipped).
+    ``per_row``: the local tensors hold one value per row (row-wise optimizer state); the column
+    slices of a table then contribute their width-weighted mean."""
     st = self.strategy
     collect = all_ranks or self.rank == 0
     n_tables = len(st.global_configs)
     result: List[Optional[np.ndarray]] = [None] * n_tables
-    weights = self.weights
-    n_dp, n_col = len(self.dp_layers), len(self.local_embedding_layers)
-    # replicated tables
-    for t, w in zip(st.table_groups[0], weights[:n_dp]):
-      result[t] = w.detach().float().cpu().numpy()
-    # table-parallel / column-sliced tables
-    col_weights = weights[n_dp:n_dp + n_col]
+    for t, w in zip(st.table_groups[0], dp_tensors):
+      result[t] = None if w is None else w.detach().float().cpu().numpy()
     for gt, t in enumerate(st.table_groups[1]):
       cfg = st.global_configs[t]
       rows, width = int(cfg["input_dim"]), int(cfg["output_dim"])
-      out = np.empty((rows, width), dtype=np.float32) if collect else None
+      if per_row:
+        out = np.zeros((rows, 1), dtype=np.float32) if collect else None
+      else:
+        out = np.empty((rows, width), dtype=np.float32) if collect else None
       for r, shards in enumerate(st.shards):
         for s in shards:
           if s.table != gt:
             continue
           src = None
           if r == self.rank:
-            src = col_weights[s.local_table][s.row_offset:s.row_offset + s.rows]
-          self._bcast_rows(src, s.rows, s.width, r, out, s.col_start)
+            src = col_tensors[s.local_table][s.row_offset:s.row_offset + s.rows]
+          if per_row:
+            if src is not None:
+              src = src.reshape(-1, 1)
+            part = np.empty((s.rows, 1), dtype=np.float32) if collect else None
+            self._bcast_rows(src, s.rows, 1, r, part, 0)
+            if out is not None:
+              out += part * (s.width / width)
+          else:
+            self._bcast_rows(src, s.rows, s.width, r, out, s.col_start)
       result[t] = out
-    # row-sliced tables
-    row_weights = weights[n_dp + n_col:]
     for gt, t in enumerate(st.table_groups[2]):
       cfg = st.global_configs[t]
       rows, width = int(cfg["input_dim"]), int(cfg["output_dim"])
-      out = np.empty((rows, width), dtype=np.float32) if collect else None
+      w_out = 1 if per_row else width
+      out = np.empty((rows, w_out), dtype=np.float32) if collect else None
       for r, (lo, hi) in enumerate(st.row_ranges[gt]):
-        src = row_weights[gt] if r == self.rank else None
+        src = row_tensors[gt] if r == self.rank else None
+        if src is not None and per_row:
+          src = src.reshape(-1, 1)
         sub = out[lo:hi] if out is not None else None
-        self._bcast_rows(src, hi - lo, width, r, sub, 0)
+        self._bcast_rows(src, hi - lo, w_out, r, sub, 0)
       result[t] = out
     if not collect:
       return []
-    return result  # type: ignore[return-value]
+    return result
 
   @staticmethod
   def _assign_chunked(param: torch.Tensor, row0: int, arr, chunk: int):
@@ -722,15 +745,79 @@ class DistributedEmbedding(nn.Module):
       raise ValueError(f"weight {t} has shape {tuple(arr.shape)}, expected {want}")
 
   # optimizer-state extension of the checkpoint surface (the reference does not cover it)
-  def get_optimizer_state(self) -> Dict[str, Any]:
-    if self._engine is None:
-      return {}
-    return self._engine.optimizer_state_dict()
+  def get_optimizer_state(self, all_ranks: bool = False) -> Dict[str, Any]:
+    """State of the fused optimizer in the same *global, sharding independent* layout as
+    :meth:`get_weights`: ``{"kind", "step", "tables": [per table: None | [slot arrays]]}`` with
+    one ``[rows, width]`` array per state slot (Adagrad accumulator; Adam m, v) or ``[rows, 1]``
+    for row-wise Adagrad (column slices of a table contribute the width-weighted mean of their
+    accumulators).  A state written by 8 column-sliced ranks loads on 4, or on one GPU.
+    Replicated tables are trained by the dense optimizer and have no entry (None).  Collective:
+    every rank must call it; only rank 0 receives the arrays unless ``all_ranks``."""
+    opt = self._fused_optimizer
+    eng = self._engine
+    if opt is None or eng is None or not eng.opt_state:
+      return {"kind": opt["kind"] if opt else None, "step": eng.step_count() if eng else 0,
+              "tables": None}
+    kind = opt["kind"]
+    n_col = len(self.local_embedding_layers)
+    n_slots = len(next(iter(eng.opt_state.values())))
+    per_row = kind == "rowwise_adagrad"
+    slots = []
+    for k in range(n_slots):
+      col = [eng.opt_state[m][k] for m in range(n_col)]
+      row = [eng.opt_state[n_col + j][k] for j in range(len(self.row_layers))]
+      slots.append(self._gather_global([None] * len(self.dp_layers), col, row, all_ranks,
+                                       per_row=per_row))
+    tables = None
+    if slots and slots[0]:
+      tables = [None if slots[0][t] is None else [sl[t] for sl in slots]
+                for t in range(len(self.strategy.global_configs))]
+    return {"kind": kind, "step": eng.step_count(), "tables": tables}
 
   def set_optimizer_state(self, state: Dict[str, Any]):
+    """Load a state produced by :meth:`get_optimizer_state` (any sharding) - every rank passes
+    the same global arrays and keeps its slices, like :meth:`set_weights`.  The older per-rank
+    format of ``FusedEngine.optimizer_state_dict`` is still accepted."""
     if self._engine is None:
       raise RuntimeError("run a forward pass (or build the engine) before loading optimizer state")
-    self._engine.load_optimizer_state_dict(state)
+    eng = self._engine
+    if "tables" not in state:
+      eng.load_optimizer_state_dict(state)
+      return
+    if self._fused_optimizer is None or state.get("kind") != self._fused_optimizer["kind"]:
+      raise ValueError(f"optimizer state of kind {state.get('kind')} does not match the attached "
+                       f"optimizer {self._fused_optimizer and self._fused_optimizer['kind']}")
+    if not eng.opt_state:
+      eng.reset_optimizer_state()
+    tables = state.get("tables")
+    if tables is not None:
+      st = self.strategy
+      per_row = state["kind"] == "rowwise_adagrad"
+      n_col = len(self.local_embedding_layers)
+      with torch.no_grad():
+        for s in st.shards[self.rank] if st.table_groups[1] else []:
+          t = st.table_groups[1][s.table]
+          for k, arr in enumerate(tables[t]):
+            dst = eng.opt_state[s.local_table][k][s.row_offset:s.row_offset + s.rows]
+            src = np.asarray(arr)[:, 0] if per_row else np.asarray(arr)[:, s.col_start:s.col_end]
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)))
+        for gt, t in enumerate(st.table_groups[2]):
+          lo, hi = st.row_ranges[gt][self.rank]
+          for k, arr in enumerate(tables[t]):
+            src = np.asarray(arr)[lo:hi, 0] if per_row else np.asarray(arr)[lo:hi]
+            eng.opt_state[n_col + gt][k].copy_(
+                torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)))
+    step = int(state.get("step", 0))
+    eng.step_t.fill_(float(step))
+    self._fused_optimizer["step"] = step
+    eng._tables_dirty = True
+
+  def close(self):
+    """Release the fused engine's peer-mapped buffers (collective over the process group).
+    Call it before dropping a ``DistributedEmbedding`` in a job that keeps running and builds
+    another one; the layer stays usable - buffers are re-created at the next forward."""
+    if self._engine is not None:
+      self._engine.close()
 
   def extra_repr(self):
     return (f"world_size={self.world_size}, rank={self.rank}, strategy={self.strategy.strategy}, "

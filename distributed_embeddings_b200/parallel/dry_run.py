@@ -99,6 +99,16 @@ class DryWorld:
   def barrier(self):
     self._barrier.wait(timeout=120)
 
+  def bcast(self, buf: torch.Tensor, owner: int, rank: int) -> torch.Tensor:
+    """Broadcast between the simulated ranks (threads): the cold-path collective behind
+    ``get_weights`` / ``get_optimizer_state``."""
+    if rank == owner:
+      self._bcast_slot = buf.clone()
+    self._barrier.wait(timeout=120)
+    out = self._bcast_slot.clone()
+    self._barrier.wait(timeout=120)
+    return out
+
 
 class DryBuf:
   """Stand-in for :class:`comm.SymmetricBuffer`."""
@@ -550,6 +560,7 @@ def build_engines(embeddings: Sequence[dict], world_size: int, **kwargs):
     de = DistributedEmbedding([dict(e) for e in embeddings], device="cpu", backend="torch",
                               world_size=world_size, rank=r, **kwargs)
     de.backend = "fused"
+    de._bcast_hook = world.bcast
     de._engine = _fused.FusedEngine(de, dry=DryRank(world, r))
     des.append(de)
   return world, des

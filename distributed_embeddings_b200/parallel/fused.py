@@ -216,10 +216,33 @@ class FusedEngine:
     return {"items": items, "n_items": pos, "cols": cols, "widths": widths, "width": col,
             "n_col": len(my_inputs)}
 
+  # ------------------------------------------------------------------ buffer lifecycle
+  _SYM_BUFS = ("in_buf", "split_buf", "ids_buf", "out_buf", "recv_buf", "rs_buf")
+  _SYM_VIEWS = ("in_flat", "in_views", "split_flat", "split_views", "ids_mp", "out", "recv", "rs")
+
+  def close(self):
+    """Release the symmetric buffers (collective: every rank of the group must call it at the
+    same point).  Peer mappings are closed on *all* ranks before any rank frees its memory -
+    otherwise a later cudaMalloc may hand the freed address out again while a peer still maps
+    it, and the next IPC open of that address fails ("resource already mapped")."""
+    bufs = [getattr(self, n, None) for n in self._SYM_BUFS]
+    bufs = [b for b in bufs if b is not None]
+    if bufs and self.W > 1 and not self.dry:
+      torch.cuda.synchronize(self.device)
+      for b in bufs:
+        b.close()
+      torch.distributed.barrier(group=self.de.group)
+    for n in self._SYM_BUFS + self._SYM_VIEWS:
+      if hasattr(self, n):
+        setattr(self, n, None)
+    self._key = None
+
   # ------------------------------------------------------------------ plan -> descriptors
   def _build(self, b: int, hots: Tuple[int, ...], ids64: bool):
     de, st, W, rank = self.de, self.st, self.W, self.rank
     dev = self.device
+    if self._key is not None:
+      self.close()  # new batch size / hotness: the old symmetric buffers go first
     id_dtype = torch.int64 if ids64 else torch.int32
     idsz = 8 if ids64 else 4
     B = b * W if de.dp_input else b

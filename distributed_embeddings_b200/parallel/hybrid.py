@@ -230,3 +230,72 @@ class BroadcastGlobalVariablesCallback:
 
   on_train_begin = __call__
   on_batch_end = __call__
+
+
+class SparseRowOptimizer:
+  """Row-sparse optimizer for model-parallel tables whose gradients arrive as (coalesced) sparse
+  tensors - the ``torch`` back end of :class:`DistributedEmbedding`, i.e. the NCCL-collectives
+  baseline, which has no fused update.  Same math as the fused kernels
+  (``ops/csrc/sparse_update_kernels.cu``): ``sgd`` | ``adagrad`` | ``rowwise_adagrad`` | ``adam``
+  (lazy: only the touched rows advance).  Counterpart of the Keras sparse-apply kernels the
+  reference relies on (examples/benchmarks/synthetic_models/main.py:96-101)."""
+
+  def __init__(self, params: Sequence[nn.Parameter], kind: str = "sgd", lr: float = 0.01,
+               eps: Optional[float] = None, beta1: float = 0.9, beta2: float = 0.999,
+               initial_accumulator_value: float = 0.1, weight_decay: float = 0.0):
+    kind = kind.lower()
+    if kind not in ("sgd", "adagrad", "rowwise_adagrad", "adam"):
+      raise ValueError(f"Unsupported optimizer {kind}")
+    self.params = [p for p in params if p.requires_grad]
+    self.kind, self.lr = kind, float(lr)
+    self.eps = (1e-8 if kind == "adam" else 1e-7) if eps is None else eps
+    self.beta1, self.beta2, self.weight_decay = beta1, beta2, weight_decay
+    self.step_count = 0
+    self.state = []
+    for p in self.params:
+      if kind == "adagrad":
+        self.state.append([torch.full_like(p, initial_accumulator_value)])
+      elif kind == "rowwise_adagrad":
+        self.state.append([torch.full((p.shape[0],), initial_accumulator_value, dtype=p.dtype,
+                                      device=p.device)])
+      elif kind == "adam":
+        self.state.append([torch.zeros_like(p), torch.zeros_like(p)])
+      else:
+        self.state.append([])
+
+  def set_lr(self, lr: float):
+    self.lr = float(lr)
+
+  @torch.no_grad()
+  def step(self):
+    self.step_count += 1
+    for p, st in zip(self.params, self.state):
+      g = p.grad
+      if g is None:
+        continue
+      if g.is_sparse:
+        g = g.coalesce()
+        idx, val = g.indices()[0], g.values().to(p.dtype)
+      else:
+        idx = torch.arange(p.shape[0], device=p.device)
+        val = g.to(p.dtype)
+      if self.weight_decay:
+        val = val + self.weight_decay * p[idx]
+      if self.kind == "sgd":
+        p.index_add_(0, idx, val, alpha=-self.lr)
+      elif self.kind == "adagrad":
+        acc = st[0][idx] + val * val
+        st[0][idx] = acc
+        p.index_add_(0, idx, val / (acc.sqrt() + self.eps), alpha=-self.lr)
+      elif self.kind == "rowwise_adagrad":
+        acc = st[0][idx] + (val * val).mean(dim=1)
+        st[0][idx] = acc
+        p.index_add_(0, idx, val / (acc.sqrt().unsqueeze(1) + self.eps), alpha=-self.lr)
+      else:
+        m = self.beta1 * st[0][idx] + (1 - self.beta1) * val
+        v = self.beta2 * st[1][idx] + (1 - self.beta2) * val * val
+        st[0][idx], st[1][idx] = m, v
+        b1 = 1 - self.beta1**self.step_count
+        b2 = 1 - self.beta2**self.step_count
+        p.index_add_(0, idx, (m / b1) / ((v / b2).sqrt() + self.eps), alpha=-self.lr)
+      p.grad = None

@@ -534,11 +534,14 @@ def case_fuzz(rank, world, device, backend, n_seeds=6, seed0=100, **kw):
         backend != "fused":
       opts["test_custom_layer"] = True
     try:
-      _generic_case(rank, world, device, backend, seed=seed, table_sizes=table_sizes,
-                    strategy=strategy, dp_input=dp_input, shared=rng.random() < 0.5, hotness=hot,
-                    ragged=ragged, combiner=rng.choice(["sum", "mean"]) if hot else None,
-                    global_batch=4 * world, fwd_tol=1e-5, bwd_tol=1e-4, id_dtype=id_dtype,
-                    **opts, **kw)
+      model = _generic_case(rank, world, device, backend, seed=seed, table_sizes=table_sizes,
+                            strategy=strategy, dp_input=dp_input, shared=rng.random() < 0.5,
+                            hotness=hot, ragged=ragged,
+                            combiner=rng.choice(["sum", "mean"]) if hot else None,
+                            global_batch=4 * world, fwd_tol=1e-5, bwd_tol=1e-4, id_dtype=id_dtype,
+                            **opts, **kw)
+      # many plans in one process: hand the peer-mapped buffers back in lock step
+      model.dist_embeddings.close()
     except ValueError as e:
       # infeasible plans must be rejected identically on every rank
       if "Not enough table" not in str(e):

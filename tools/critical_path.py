@@ -14,7 +14,10 @@ import json
 import re
 from collections import defaultdict
 
-WAIT_KERNELS = ("barrier_kernel", "allreduce_p2p_kernel", "allreduce_multimem_kernel")
+# kernels that wait for peers at their head (flag spins folded into the data kernels)
+WAIT_KERNELS = ("barrier_kernel", "allreduce_p2p_kernel", "allreduce_multimem_kernel",
+                "push_segments_kernel", "lookup_fwd_kernel", "interact_fwd_kernel",
+                "scatter_add_bwd_kernel", "sync_only_kernel")
 
 
 def load_kernels(path):
@@ -54,8 +57,9 @@ def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("profile", help="the --profile path given to bench.py")
   ap.add_argument("--step", type=int, default=2, help="which profiled step to print")
-  ap.add_argument("--marker", default="lookup_fwd_kernel",
-                  help="kernel that occurs once per step (splits the trace into steps)")
+  ap.add_argument("--marker", default=None,
+                  help="kernel that occurs once per step (splits the trace into steps); default: "
+                       "push_segments_kernel if present (multi-GPU), else lookup_fwd_kernel")
   ap.add_argument("--gap-us", type=float, default=3.0, help="report idle gaps above this")
   args = ap.parse_args()
 
@@ -64,7 +68,10 @@ def main():
     paths[int(re.search(r"\.rank(\d+)\.trace\.json$", p).group(1))] = p
   per_rank = {}
   for r, p in sorted(paths.items()):
-    steps = split_steps(load_kernels(p), args.marker)
+    ks_all = load_kernels(p)
+    marker = args.marker or ("push_segments_kernel" if any(
+        "push_segments_kernel" in k["name"] for k in ks_all) else "lookup_fwd_kernel")
+    steps = split_steps(ks_all, marker)
     per_rank[r] = steps[min(args.step, len(steps) - 1)]
 
   # ranks have their own clocks only if they are different hosts; one host -> one CUPTI clock
