@@ -411,6 +411,7 @@ class DLRMTrainStep:
       # is zero while warming up so the extra passes leave the weights untouched.
       self.lr_t.zero_()
       self.engine.update_lr(0.0)
+      self.engine.dry_updates(True)  # optimizer state (Adagrad / Adam) stays untouched as well
       s = torch.cuda.Stream(device=self.dev)
       s.wait_stream(torch.cuda.current_stream())
       with torch.cuda.stream(s):
@@ -418,6 +419,7 @@ class DLRMTrainStep:
           self._step_impl()
       torch.cuda.current_stream().wait_stream(s)
       torch.cuda.synchronize()
+      self.engine.dry_updates(False)
       g = torch.cuda.CUDAGraph()
       with torch.cuda.graph(g):
         self._step_impl()

@@ -174,11 +174,12 @@ int bit_length(int64_t v) {
 
 // Build (row key, item) pairs for every looked-up id, sort by key, and find the unique rows.
 // Returns (sorted_keys, sorted_items, seg_start, n_unique[1]); nothing is copied to the host.
-// DE_B200_SORT=own routes the deduplicated update through radix_sort.cu instead of CUB
+// The first-party radix sort / head compaction (radix_sort.cu) is the default; DE_B200_SORT=cub
+// routes the deduplicated update through the CUB calls of the CUDA toolkit instead (A/B only)
 bool use_own_sort() {
   static const bool own = [] {
     const char* v = std::getenv("DE_B200_SORT");
-    return v != nullptr && std::string(v) == "own";
+    return !(v != nullptr && std::string(v) == "cub");
   }();
   return own;
 }
@@ -205,6 +206,31 @@ std::tuple<Tensor, Tensor> radix_sort_pairs(const Tensor& keys, const Tensor& it
   check_launch();
   if (where == 0) return {ka, ia};
   return {kb, ib};
+}
+
+// (int32 keys in [0, 2^32) read as unsigned, int32 items) -> (int64 sorted keys, sorted items)
+std::tuple<Tensor, Tensor> radix_sort_pairs32(const Tensor& keys, const Tensor& items,
+                                              int64_t end_bit) {
+  TORCH_CHECK(keys.is_cuda() && keys.scalar_type() == at::kInt && keys.is_contiguous());
+  TORCH_CHECK(items.is_cuda() && items.scalar_type() == at::kInt && items.is_contiguous() &&
+              items.numel() == keys.numel());
+  c10::cuda::CUDAGuard guard(keys.device());
+  const int64_t n = keys.numel();
+  TORCH_CHECK(n < (int64_t(1) << 31), "own radix sort: too many items");
+  Tensor ka = keys.clone(), ia = items.clone();
+  Tensor kb = at::empty_like(ka), ib = at::empty_like(ia);
+  Tensor out = at::empty({n}, keys.options().dtype(at::kLong));
+  if (n == 0) return {out, ia};
+  Tensor temp = at::empty({static_cast<int64_t>(de::radix_sort_temp_bytes(n))},
+                          at::TensorOptions().device(keys.device()).dtype(at::kByte));
+  int where = de::radix_sort_pairs32(
+      temp.data_ptr(), reinterpret_cast<uint32_t*>(ka.data_ptr<int>()),
+      reinterpret_cast<uint32_t*>(ia.data_ptr<int>()),
+      reinterpret_cast<uint32_t*>(kb.data_ptr<int>()),
+      reinterpret_cast<uint32_t*>(ib.data_ptr<int>()), out.data_ptr<int64_t>(), n,
+      static_cast<int>(end_bit), cur_stream());
+  check_launch();
+  return {out, where == 0 ? ia : ib};
 }
 
 std::tuple<Tensor, Tensor> head_segments(const Tensor& sorted_keys) {
@@ -245,6 +271,38 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> sort_items(const Tensor& descs, const
   Tensor seg_start = at::empty({n_items + 1}, i64);
   Tensor n_unique = at::zeros({1}, i64);
   if (n_items == 0) return {keys_sorted, items_sorted, seg_start, n_unique};
+  if (use_own_sort() && total_rows < (int64_t(1) << 32) - 1) {
+    // every key (and the sentinel = total_rows) fits 32 bits: sort (uint32, uint32) pairs, the
+    // last pass widens the keys for the update kernels
+    TORCH_CHECK(n_items < (int64_t(1) << 31), "own radix sort: too many items");
+    Tensor k32a = prefill_sentinel
+                      ? at::full({n_items}, static_cast<int64_t>(static_cast<int32_t>(
+                                                static_cast<uint32_t>(total_rows))), i32)
+                      : at::empty({n_items}, i32);
+    Tensor k32b = at::empty({n_items}, i32);
+    de::launch_build_keys(reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
+                          reinterpret_cast<const de::TableDesc*>(tables.data_ptr()),
+                          static_cast<int>(n_tables), static_cast<int>(n_inputs), batch,
+                          src_batch, to_peers(src_ptrs), ids64, k32a.data_ptr(),
+                          reinterpret_cast<uint32_t*>(items.data_ptr<int>()), sm_count(), stream,
+                          true);
+    check_launch();
+    size_t sort_bytes = de::radix_sort_temp_bytes(n_items);
+    size_t head_bytes = de::head_segments_temp_bytes(n_items);
+    Tensor temp = at::empty({static_cast<int64_t>(std::max(sort_bytes, head_bytes))},
+                            at::TensorOptions().device(descs.device()).dtype(at::kByte));
+    int where = de::radix_sort_pairs32(
+        temp.data_ptr(), reinterpret_cast<uint32_t*>(k32a.data_ptr<int>()),
+        reinterpret_cast<uint32_t*>(items.data_ptr<int>()),
+        reinterpret_cast<uint32_t*>(k32b.data_ptr<int>()),
+        reinterpret_cast<uint32_t*>(items_sorted.data_ptr<int>()),
+        keys_sorted.data_ptr<int64_t>(), n_items, bit_length(total_rows), stream);
+    if (where == 0) std::swap(items, items_sorted);
+    de::head_segments(temp.data_ptr(), keys_sorted.data_ptr<int64_t>(), n_items,
+                      seg_start.data_ptr<int64_t>(), n_unique.data_ptr<int64_t>(), stream);
+    check_launch();
+    return {keys_sorted, items_sorted, seg_start, n_unique};
+  }
   de::launch_build_keys(reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
                         reinterpret_cast<const de::TableDesc*>(tables.data_ptr()),
                         static_cast<int>(n_tables), static_cast<int>(n_inputs), batch, src_batch,
@@ -541,6 +599,23 @@ void allreduce(at::IntArrayRef buf_ptrs, at::IntArrayRef flag_ptrs, Tensor epoch
   check_launch();
 }
 
+void p2p_store_bench(const Tensor& src, int64_t dst_ptr, int64_t n_rows, int64_t row_bytes,
+                     int64_t vec_bytes, int64_t dst_stride, int64_t unroll, int64_t blocks,
+                     int64_t threads) {
+  TORCH_CHECK(src.is_cuda() && src.is_contiguous() &&
+              src.numel() * src.element_size() >= n_rows * row_bytes);
+  TORCH_CHECK(row_bytes % vec_bytes == 0 && (vec_bytes == 4 || vec_bytes == 8 || vec_bytes == 16));
+  TORCH_CHECK((row_bytes / vec_bytes >= 32 && (row_bytes / vec_bytes) % 32 == 0) ||
+              32 % (row_bytes / vec_bytes) == 0);
+  TORCH_CHECK(unroll >= 1 && unroll <= 8 && threads % 32 == 0 && threads <= 1024);
+  c10::cuda::CUDAGuard guard(src.device());
+  de::launch_p2p_store_bench(src.data_ptr(), reinterpret_cast<void*>(dst_ptr), n_rows,
+                             static_cast<int>(row_bytes), static_cast<int>(vec_bytes), dst_stride,
+                             static_cast<int>(unroll), static_cast<int>(blocks),
+                             static_cast<int>(threads), cur_stream());
+  check_launch();
+}
+
 // segs[j] = {dst_rank, src_elem_off, dst_elem_off, n_elems}: push id segments to their owners
 void push_segments(const Tensor& segs, const Tensor& src, at::IntArrayRef dst_ptrs,
                    int64_t max_seg_elems, at::IntArrayRef sync) {
@@ -692,6 +767,35 @@ void interact_bwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, const 
                                     static_cast<int>(n_routes), to_sync(sync));
   TORCH_CHECK(ok, "unsupported interaction shape (n_emb <= 31, dim in {32,64,128}; routed / "
                   "signalling launches need dim in {64,128} and 16-byte aligned rows)");
+  check_launch();
+}
+
+// out[:, :out_len] = avg_pool1d(x[:, :n], stride) with "same" padding (bf16, unit inner strides)
+void avgpool_fwd(const Tensor& x, int64_t n, Tensor out, int64_t stride) {
+  check_bf16_2d(x, "x");
+  check_bf16_2d(out, "out");
+  const int64_t out_len = (n + stride - 1) / stride;
+  TORCH_CHECK(x.size(1) >= n && out.size(1) >= out_len && out.size(0) == x.size(0));
+  const int64_t pad = std::max<int64_t>(0, (out_len - 1) * stride + stride - n);
+  c10::cuda::CUDAGuard guard(x.device());
+  de::launch_avgpool_fwd(x.data_ptr(), x.stride(0), static_cast<int>(n), out.data_ptr(),
+                         out.stride(0), static_cast<int>(out_len), static_cast<int>(stride),
+                         static_cast<int>(pad / 2), x.size(0), cur_stream());
+  check_launch();
+}
+
+// dx[:, :n] = gradient of avgpool_fwd for dout[:, :out_len]
+void avgpool_bwd(const Tensor& dout, Tensor dx, int64_t n, int64_t stride) {
+  check_bf16_2d(dout, "dout");
+  check_bf16_2d(dx, "dx");
+  const int64_t out_len = (n + stride - 1) / stride;
+  TORCH_CHECK(dx.size(1) >= n && dout.size(1) >= out_len && dout.size(0) == dx.size(0));
+  const int64_t pad = std::max<int64_t>(0, (out_len - 1) * stride + stride - n);
+  c10::cuda::CUDAGuard guard(dx.device());
+  de::launch_avgpool_bwd(dout.data_ptr(), dout.stride(0), static_cast<int>(out_len),
+                         dx.data_ptr(), dx.stride(0), static_cast<int>(n),
+                         static_cast<int>(stride), static_cast<int>(pad / 2), dx.size(0),
+                         cur_stream());
   check_launch();
 }
 
@@ -865,6 +969,8 @@ TORCH_LIBRARY(de_b200, m) {
       &sort_items);
   m.def("radix_sort_pairs(Tensor keys, Tensor items, int end_bit) -> (Tensor, Tensor)",
         &radix_sort_pairs);
+  m.def("radix_sort_pairs32(Tensor keys, Tensor items, int end_bit) -> (Tensor, Tensor)",
+        &radix_sort_pairs32);
   m.def("head_segments(Tensor sorted_keys) -> (Tensor, Tensor)", &head_segments);
   m.def(
       "segment_update(Tensor descs, Tensor tables, int n_tables, int batch, int grad_batch, "
@@ -904,6 +1010,10 @@ TORCH_LIBRARY(de_b200, m) {
   m.def("gather_segments(Tensor segs, int[] src_ptrs, Tensor(a!) dst, int max_seg_elems) -> ()",
         &gather_segments);
   m.def(
+      "p2p_store_bench(Tensor src, int dst_ptr, int n_rows, int row_bytes, int vec_bytes, "
+      "int dst_stride, int unroll, int blocks, int threads) -> ()",
+      &p2p_store_bench);
+  m.def(
       "push_segments(Tensor segs, Tensor src, int[] dst_ptrs, int max_seg_elems, int[] sync) -> ()",
       &push_segments);
   m.def(
@@ -929,6 +1039,8 @@ TORCH_LIBRARY(de_b200, m) {
       "int demb_ptr, int demb_stride, float emb_grad_scale, Tensor? routes, int n_routes, "
       "int[] sync) -> ()",
       &interact_bwd);
+  m.def("avgpool_fwd(Tensor x, int n, Tensor(a!) out, int stride) -> ()", &avgpool_fwd);
+  m.def("avgpool_bwd(Tensor dout, Tensor(a!) dx, int n, int stride) -> ()", &avgpool_bwd);
   m.def("relu_bwd_bias(Tensor(a!) dy, Tensor y, Tensor(b!) db) -> ()", &relu_bwd_bias);
   m.def(
       "head_loss(Tensor x, Tensor w, Tensor bias, Tensor labels, float inv_batch, Tensor(a!) dx, "

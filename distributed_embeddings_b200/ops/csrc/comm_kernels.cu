@@ -205,6 +205,46 @@ allreduce_multimem_kernel(void* mc_ptr, const __grid_constant__ PeerPtrs flags, 
                          timeout_cycles, error_flag);
 }
 
+// ----------------------------------------------------------------------------- P2P store probe
+// Micro-benchmark of kernel-issued stores into peer memory (tools/bench_p2p_store.py): row r of a
+// contiguous local buffer goes to dst + r * dst_stride.  VEC bytes per lane; a warp instruction
+// covers 32 * VEC contiguous bytes of one row (or several whole rows when the row is shorter),
+// which is exactly how the lookup / gradient-push kernels emit their rows.
+template <typename V>
+__global__ void __launch_bounds__(1024)
+p2p_store_bench_kernel(const char* __restrict__ src, char* __restrict__ dst, int64_t n_rows,
+                       int row_bytes, int64_t dst_stride, int unroll) {
+  constexpr int VB = sizeof(V);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int lanes_per_row = row_bytes / VB;  // <= 32 handled as several rows per instruction
+  if (lanes_per_row >= 32) {
+    const int chunks = lanes_per_row / 32;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+      const V* sp = reinterpret_cast<const V*>(src + r * row_bytes);
+      V* dp = reinterpret_cast<V*>(dst + r * dst_stride);
+      for (int c = 0; c < chunks; ++c) dp[c * 32 + lane] = sp[c * 32 + lane];
+    }
+  } else {
+    const int rpi = 32 / lanes_per_row;  // rows per instruction
+    const int sub = lane / lanes_per_row, li = lane - sub * lanes_per_row;
+    for (int64_t r0 = warp * rpi * unroll; r0 < n_rows; r0 += n_warps * rpi * unroll) {
+      V v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t r = r0 + u * rpi + sub;
+        if (u < unroll && r < n_rows) v[u] = reinterpret_cast<const V*>(src + r * row_bytes)[li];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t r = r0 + u * rpi + sub;
+        if (u < unroll && r < n_rows) reinterpret_cast<V*>(dst + r * dst_stride)[li] = v[u];
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- signalling only
 __global__ void sync_only_kernel(const __grid_constant__ SyncArgs sync) {
   sync_head(sync);
@@ -572,6 +612,22 @@ void launch_copy_cast_2d(const void* src, int64_t src_stride, void* dst, int64_t
   else DE_CC_D(float);
 #undef DE_CC_D
 #undef DE_CC
+}
+
+void launch_p2p_store_bench(const void* src, void* dst, int64_t n_rows, int row_bytes,
+                            int vec_bytes, int64_t dst_stride, int unroll, int blocks, int threads,
+                            cudaStream_t stream) {
+  const char* s = static_cast<const char*>(src);
+  char* d = static_cast<char*>(dst);
+  if (vec_bytes == 16)
+    p2p_store_bench_kernel<uint4><<<blocks, threads, 0, stream>>>(s, d, n_rows, row_bytes,
+                                                                  dst_stride, unroll);
+  else if (vec_bytes == 8)
+    p2p_store_bench_kernel<uint2><<<blocks, threads, 0, stream>>>(s, d, n_rows, row_bytes,
+                                                                  dst_stride, unroll);
+  else
+    p2p_store_bench_kernel<uint32_t><<<blocks, threads, 0, stream>>>(s, d, n_rows, row_bytes,
+                                                                     dst_stride, unroll);
 }
 
 void launch_sync_only(const SyncArgs& sync, cudaStream_t stream) {

@@ -118,9 +118,10 @@ void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch,
                             cudaStream_t stream, bool vec8, const SyncArgs& sync);
 
 // ---- backward: sorted / deduplicated path -----------------------------------------------
+// keys32: `keys` points at uint32 keys (every key incl. the sentinel fits 32 bits)
 void launch_build_keys(const InputDesc* descs, const TableDesc* tables, int n_tables, int n_inputs,
-                       int64_t batch, int64_t src_batch, const PeerPtrs& src, bool ids64, int64_t* keys,
-                       uint32_t* items, int sm_count, cudaStream_t stream);
+                       int64_t batch, int64_t src_batch, const PeerPtrs& src, bool ids64, void* keys,
+                       uint32_t* items, int sm_count, cudaStream_t stream, bool keys32 = false);
 size_t sort_pairs_temp_bytes(int64_t n);
 void sort_pairs(void* temp, size_t temp_bytes, const int64_t* keys_in, int64_t* keys_out,
                 const uint32_t* items_in, uint32_t* items_out, int64_t n, int end_bit,
@@ -133,6 +134,9 @@ void unique_segments(void* temp, size_t temp_bytes, const int64_t* sorted_keys, 
 size_t radix_sort_temp_bytes(int64_t n);
 int radix_sort_pairs(void* temp, int64_t* keys_a, uint32_t* items_a, int64_t* keys_b,
                      uint32_t* items_b, int64_t n, int end_bit, cudaStream_t stream);
+int radix_sort_pairs32(void* temp, uint32_t* keys_a, uint32_t* items_a, uint32_t* keys_b,
+                       uint32_t* items_b, int64_t* keys_out64, int64_t n, int end_bit,
+                       cudaStream_t stream);
 size_t head_segments_temp_bytes(int64_t n);
 void head_segments(void* temp, const int64_t* sorted_keys, int64_t n, int64_t* seg_start,
                    int64_t* n_unique, cudaStream_t stream);
@@ -175,6 +179,10 @@ void launch_allreduce_multimem(void* mc_ptr, const PeerPtrs& flags, uint32_t* ep
                                int world, int64_t n_elems, float scale, bool bf16, int channel,
                                unsigned long long timeout_cycles, int* error_flag, int sm_count,
                                cudaStream_t stream, int max_blocks = 0);
+// Micro-benchmark of kernel-issued row stores into (peer) memory, see comm_kernels.cu
+void launch_p2p_store_bench(const void* src, void* dst, int64_t n_rows, int row_bytes,
+                            int vec_bytes, int64_t dst_stride, int unroll, int blocks, int threads,
+                            cudaStream_t stream);
 // Standalone signalling kernel (one block): the wait / signal parts of `sync` without any data.
 void launch_sync_only(const SyncArgs& sync, cudaStream_t stream);
 // Segmented P2P *push* of index segments into the owners' id buffers (the reference's
@@ -224,6 +232,12 @@ bool launch_interact_bwd(const void* bottom, int64_t bottom_stride, const void* 
                          int64_t demb_stride, float emb_grad_scale, int64_t batch, int sm_count,
                          cudaStream_t stream, const GradRoute* routes, int n_routes,
                          const SyncArgs& sync);
+// 1-D average pooling over bf16 rows ("same" padding; the synthetic models' interaction)
+void launch_avgpool_fwd(const void* x, int64_t x_stride, int n, void* out, int64_t out_stride,
+                        int out_len, int stride, int left, int64_t rows, cudaStream_t stream);
+void launch_avgpool_bwd(const void* dout, int64_t dout_stride, int out_len, void* dx,
+                        int64_t dx_stride, int n, int stride, int left, int64_t rows,
+                        cudaStream_t stream);
 void launch_relu_bwd_bias(void* dy, const void* y, float* db, int64_t rows, int cols,
                           cudaStream_t stream);
 bool launch_head_loss(const void* x, int K, const void* w, const void* bias, const float* labels,

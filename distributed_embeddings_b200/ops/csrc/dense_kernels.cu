@@ -617,7 +617,67 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, int src_cols, bf1
   }
 }
 
+// ---- 1-D average pooling over the concatenated embeddings ("same" padding, partial windows
+// divide by the number of real elements): the memory-bound stand-in for FM / pooling
+// interactions in the synthetic models (reference synthetic_models.py:150-160, Keras
+// AveragePooling1D).  out[r, j] = mean(x[r, j*stride-left : (j+1)*stride-left] ∩ [0, n)).
+__global__ void __launch_bounds__(256)
+avgpool_fwd_kernel(const bf16* __restrict__ x, int64_t x_stride, int n, bf16* __restrict__ out,
+                   int64_t out_stride, int out_len, int stride, int left, int64_t rows) {
+  const int64_t total = rows * out_len;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += step) {
+    const int64_t r = i / out_len;
+    const int j = static_cast<int>(i - r * out_len);
+    const int lo = max(0, j * stride - left), hi = min(n, (j + 1) * stride - left);
+    const bf16* xp = x + r * x_stride;
+    float acc = 0.f;
+    for (int c = lo; c < hi; ++c) acc += __bfloat162float(xp[c]);
+    out[r * out_stride + j] = __float2bfloat16_rn(hi > lo ? acc / static_cast<float>(hi - lo) : 0.f);
+  }
+}
+
+// dx[r, c] = dout[r, window(c)] / count(window(c))
+__global__ void __launch_bounds__(256)
+avgpool_bwd_kernel(const bf16* __restrict__ dout, int64_t dout_stride, int out_len,
+                   bf16* __restrict__ dx, int64_t dx_stride, int n, int stride, int left,
+                   int64_t rows) {
+  const int64_t total = rows * n;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += step) {
+    const int64_t r = i / n;
+    const int c = static_cast<int>(i - r * n);
+    const int j = (c + left) / stride;
+    const int lo = max(0, j * stride - left), hi = min(n, (j + 1) * stride - left);
+    const float g = j < out_len ? __bfloat162float(dout[r * dout_stride + j]) : 0.f;
+    dx[r * dx_stride + c] = __float2bfloat16_rn(g / static_cast<float>(hi - lo));
+  }
+}
+
 }  // namespace
+
+void launch_avgpool_fwd(const void* x, int64_t x_stride, int n, void* out, int64_t out_stride,
+                        int out_len, int stride, int left, int64_t rows, cudaStream_t stream) {
+  if (rows <= 0 || out_len <= 0) return;
+  int64_t blocks = (rows * out_len + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  avgpool_fwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(x), x_stride, n, reinterpret_cast<bf16*>(out), out_stride,
+      out_len, stride, left, rows);
+}
+
+void launch_avgpool_bwd(const void* dout, int64_t dout_stride, int out_len, void* dx,
+                        int64_t dx_stride, int n, int stride, int left, int64_t rows,
+                        cudaStream_t stream) {
+  if (rows <= 0 || n <= 0) return;
+  int64_t blocks = (rows * n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  avgpool_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(dout), dout_stride, out_len, reinterpret_cast<bf16*>(dx),
+      dx_stride, n, stride, left, rows);
+}
 
 bool launch_interact_fwd(const void* bottom, int64_t bottom_stride, const void* emb,
                          int64_t emb_stride, int n_emb, int dim, void* z, int64_t z_stride,

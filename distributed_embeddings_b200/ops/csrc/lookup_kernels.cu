@@ -269,6 +269,42 @@ scatter_add_bwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_
       }
     }
 
+    // one-hot inputs: the tile's 32 ids come with one coalesced load and are handed out by
+    // shuffle, so the reductions do not wait for a dependent per-row id load
+    const bool onehot = (D.hotness == 1) && (D.offsets == nullptr);
+    long long tile_id = -1;
+    if (onehot && lane < tc.nsamp) {
+      int n0;
+      const IdT* p0 = rd.sample(tc.g0 + lane, n0);
+      tile_id = static_cast<long long>(*p0) + D.id_shift;
+    }
+    if (onehot) {
+      for (int c0 = 0; c0 < nvec; c0 += lpr) {
+        const int cv = c0 + li;
+        const bool col_ok = cv < nvec;
+        const int col = cv * VEC;
+        for (int r0 = 0; r0 < tc.nsamp; r0 += rpw * kUnroll) {
+          FVec<VEC> g[kUnroll];
+          int64_t id[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const int r = r0 + u * rpw + sub;
+            const int64_t idr = __shfl_sync(0xffffffffu, tile_id, r & 31);
+            id[u] = -1;
+            if (r < tc.nsamp && col_ok &&
+                static_cast<uint64_t>(idr) < static_cast<uint64_t>(D.sub_rows)) {
+              id[u] = idr;
+              g[u] = ld_act<GradT, VEC>(grad_base + (i0 + r) * grad_stride + D.dst_col + col);
+              g[u].scale(scale);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (id[u] >= 0) red_add_f32<VEC>(table + (D.row_base + id[u]) * W + col, g[u]);
+        }
+      }
+      continue;
+    }
     for (int c0 = 0; c0 < nvec; c0 += lpr) {
       const int cv = c0 + li;
       const bool col_ok = cv < nvec;

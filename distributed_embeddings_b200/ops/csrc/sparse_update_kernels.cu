@@ -39,11 +39,11 @@ __device__ __forceinline__ const IdT* sample_ids(const InputDesc& D, const PeerP
 
 // key = global row (table key_base + fused row), item = f * batch + g.  Out-of-range ids get the
 // sentinel key (= total rows) and sort to the end; the sort only needs log2(total rows + 1) bits.
-template <typename IdT>
+template <typename IdT, typename KeyT>
 __global__ void __launch_bounds__(kThreads)
 build_keys_kernel(const InputDesc* __restrict__ descs, const TableDesc* __restrict__ tables,
                   int n_tables, int n_inputs, int64_t batch, int64_t src_batch,
-                  const __grid_constant__ PeerPtrs src, int64_t* __restrict__ keys,
+                  const __grid_constant__ PeerPtrs src, KeyT* __restrict__ keys,
                   uint32_t* __restrict__ items) {
   const int64_t tiles_per_input = (batch + kTile - 1) / kTile;
   const int64_t total = tiles_per_input * n_inputs;
@@ -65,7 +65,7 @@ build_keys_kernel(const InputDesc* __restrict__ descs, const TableDesc* __restri
     for (int h = 0; h < n; ++h) {
       const int64_t id = static_cast<int64_t>(p[h]) + D.id_shift;
       const bool ok = static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows);
-      keys[first + h] = ok ? key_base + D.row_base + id : sentinel;
+      keys[first + h] = static_cast<KeyT>(ok ? key_base + D.row_base + id : sentinel);
       items[first + h] = item;
     }
   }
@@ -499,18 +499,23 @@ int grid_cap(int64_t work_warps, int sm_count, int per_sm) {
 }  // namespace
 
 void launch_build_keys(const InputDesc* descs, const TableDesc* tables, int n_tables, int n_inputs,
-                       int64_t batch,
-                       int64_t src_batch, const PeerPtrs& src, bool ids64, int64_t* keys,
-                       uint32_t* items, int sm_count, cudaStream_t stream) {
+                       int64_t batch, int64_t src_batch, const PeerPtrs& src, bool ids64, void* keys,
+                       uint32_t* items, int sm_count, cudaStream_t stream, bool keys32) {
   if (n_inputs <= 0 || batch <= 0) return;
   const int64_t tiles = ((batch + kTile - 1) / kTile) * n_inputs;
   const int grid = grid_cap(tiles, sm_count, 8);
-  if (ids64)
-    build_keys_kernel<int64_t><<<grid, kThreads, 0, stream>>>(descs, tables, n_tables, n_inputs,
-                                                              batch, src_batch, src, keys, items);
-  else
-    build_keys_kernel<int32_t><<<grid, kThreads, 0, stream>>>(descs, tables, n_tables, n_inputs,
-                                                              batch, src_batch, src, keys, items);
+#define DE_BK(IdT, KeyT)                                                                      \
+  build_keys_kernel<IdT, KeyT><<<grid, kThreads, 0, stream>>>(                                \
+      descs, tables, n_tables, n_inputs, batch, src_batch, src, reinterpret_cast<KeyT*>(keys), \
+      items)
+  if (keys32) {
+    if (ids64) DE_BK(int64_t, uint32_t);
+    else DE_BK(int32_t, uint32_t);
+  } else {
+    if (ids64) DE_BK(int64_t, int64_t);
+    else DE_BK(int32_t, int64_t);
+  }
+#undef DE_BK
 }
 
 size_t sort_pairs_temp_bytes(int64_t n) {

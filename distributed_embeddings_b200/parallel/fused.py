@@ -142,6 +142,8 @@ class FusedEngine:
     self._tables_dirty = True
     self._dp_targets = None
     self._dp_target_desc = None
+    self.out_row_stride = None  # see set_out_row_stride
+    self._dry_updates = False   # see dry_updates()
     # local model-parallel tables: table-parallel first, then row slices
     self.mp_layers = list(de.local_embedding_layers) + list(de.row_layers)
     self.n_col_tables = len(de.local_embedding_layers)
@@ -153,6 +155,25 @@ class FusedEngine:
 
   def _sync(self, wait: int = -1, wait_abs: int = -1, signal: int = -1):
     return self.ctx.sync(wait=wait, wait_abs=wait_abs, signal=signal) if self.W > 1 else []
+
+  def dry_updates(self, on: bool):
+    """While on, the update kernels run on a zero gradient (scale 0) and the optimizer step
+    counter is left alone: the warm-up passes a trainer runs before capturing its CUDA graph
+    exercise every kernel (lazy module loading, workspaces) without touching the tables or the
+    optimizer state (Adagrad accumulators would otherwise absorb the warm-up gradients)."""
+    self._dry_updates = bool(on)
+
+  def set_out_row_stride(self, stride: Optional[int]):
+    """Row stride (elements, multiple of 8) of the output buffer, >= sum of the output widths.
+    A consumer that concatenates the embeddings with other features (the synthetic models' MLP
+    input) lets the lookups write straight into its input matrix: ``out_full`` is the whole
+    ``[batch, stride]`` buffer, ``out`` the ``[batch, sum(widths)]`` view of its first columns."""
+    if stride is not None and (stride < self.total_width or stride % 8):
+      raise ValueError("out row stride must be a multiple of 8 and >= the total output width")
+    if stride != self.out_row_stride:
+      self.out_row_stride = stride
+      if self._key is not None:
+        self.close()
 
   # ------------------------------------------------------------------ capabilities
   def busy(self) -> bool:
@@ -218,7 +239,8 @@ class FusedEngine:
 
   # ------------------------------------------------------------------ buffer lifecycle
   _SYM_BUFS = ("in_buf", "split_buf", "ids_buf", "out_buf", "recv_buf", "rs_buf")
-  _SYM_VIEWS = ("in_flat", "in_views", "split_flat", "split_views", "ids_mp", "out", "recv", "rs")
+  _SYM_VIEWS = ("in_flat", "in_views", "split_flat", "split_views", "ids_mp", "out", "out_full",
+                "recv", "rs")
 
   def close(self):
     """Release the symmetric buffers (collective: every rank of the group must call it at the
@@ -347,18 +369,21 @@ class FusedEngine:
 
     # --- output buffer (requester side) and gradient receive buffer (owner side)
     tw = self.total_width
-    out_bytes = max(lb * tw * csz, 16)
+    ostride = self.out_stride = int(self.out_row_stride or tw)
+    out_bytes = max(lb * ostride * csz, 16)
     recv_w_sym = max(max(l["width"] for l in layouts), 1)
     if W > 1:
       self.out_buf = self.ctx.alloc(out_bytes, "emb_out")
-      self.out = self.out_buf.view(self.compute_dtype, (lb, tw))
+      self.out_full = self.out_buf.view(self.compute_dtype, (lb, ostride))
+      self.out = self.out_full[:, :tw]
       self.out_ptrs = self.out_buf.peer_ptrs()
       self.recv_buf = self.ctx.alloc(max(B * recv_w_sym * csz, 16), "emb_grad_recv")
       self.recv = self.recv_buf.view(self.compute_dtype, (B, self.recv_width))
       recv_ptrs = self.recv_buf.peer_ptrs()
     else:
       self.out_buf = self.recv_buf = None
-      self.out = torch.zeros(lb, tw, dtype=self.compute_dtype, device=dev)
+      self.out_full = torch.zeros(lb, ostride, dtype=self.compute_dtype, device=dev)
+      self.out = self.out_full[:, :tw]
       self.out_ptrs = [self.out.data_ptr()]
       self.recv = torch.zeros(B, self.recv_width, dtype=self.compute_dtype, device=dev)
       recv_ptrs = [self.recv.data_ptr()]
@@ -550,7 +575,7 @@ class FusedEngine:
     cols = [int(x) for x in list(self.fwd_main_np["dst_col"]) + list(self.fwd_rs_np["dst_col"]) +
             list(ddesc["dst_col"]) + list(mp["dst_col"])]
     self.vec4 = all(w % 4 == 0 for w in widths) and all(c % 4 == 0 for c in cols) and \
-        tw % 4 == 0 and self.rs_width % 4 == 0 and self.recv_width % 4 == 0
+        tw % 4 == 0 and self.rs_width % 4 == 0 and self.recv_width % 4 == 0 and ostride % 4 == 0
     # 16-byte gradient loads (8 columns per lane) in the SGD update: DE_B200_VEC8_GRAD=1
     self.vec8 = os.environ.get("DE_B200_VEC8_GRAD", "0") == "1" and self.vec4 and \
         all(w % 8 == 0 for w in widths) and all(c % 8 == 0 for c in cols) and \
@@ -757,11 +782,11 @@ class FusedEngine:
         ops.sync_only(self._sync(signal=CH_IDS))
         wait_ids = CH_IDS
     if self.ddesc is not None:
-      ops.lookup_fwd(self.ddesc, len(self.ddesc_np), lb, lb, lb, self.total_width, [],
+      ops.lookup_fwd(self.ddesc, len(self.ddesc_np), lb, lb, lb, self.out_stride, [],
                      [self.out.data_ptr()], 0, self.ids64, self.act, self.vec4, [])
     if self.fwd_main is not None:
       sig = CH_OUT if self.fwd_rs is None else -1
-      ops.lookup_fwd(self.fwd_main, len(self.fwd_main_np), B, B, lb, self.total_width, [],
+      ops.lookup_fwd(self.fwd_main, len(self.fwd_main_np), B, B, lb, self.out_stride, [],
                      self.out_ptrs, rank, self.ids64, self.act, self.vec4,
                      self._sync(wait=wait_ids, signal=sig))
       wait_ids = -1  # later launches of this stream are ordered behind the wait
@@ -779,7 +804,7 @@ class FusedEngine:
     if self.W > 1 and self.has_mp:
       self.ops.sync_only(self._sync(wait=CH_OUT))
     if self.rs_buf is not None:
-      self.ops.rowslice_reduce(self.rs, self.out.data_ptr(), self.total_width, self.act,
+      self.ops.rowslice_reduce(self.rs, self.out.data_ptr(), self.out_stride, self.act,
                                self.rs_cols_t)
 
   # ------------------------------------------------------------------ backward
@@ -878,11 +903,12 @@ class FusedEngine:
     if self._tables_dirty:
       self._refresh_tables()
     B = self.B
+    gscale = 0.0 if self._dry_updates else de.mp_grad_scale
     if opt is not None and opt["kind"] == "sgd" and not opt.get("deterministic", False) and \
         not self.has_offload:
       # head: every requester's gradient rows have landed; tail: ids + gradients are consumed
       ops.scatter_add_bwd(self.mpdesc, self.n_mp_inputs, B, B, B, self.recv_width, [],
-                          self.recv_ptr, 0, -de.mp_grad_scale, self.lr_t.data_ptr(), self.ids64,
+                          self.recv_ptr, 0, -gscale, self.lr_t.data_ptr(), self.ids64,
                           self.act, self.vec4, self.vec8,
                           self._sync(wait=CH_GRAD, signal=CH_CONSUMED))
       return [None] * n_mp
@@ -892,10 +918,14 @@ class FusedEngine:
                                                 B, B, [], self.ids64, self.n_items,
                                                 self.total_rows, self.any_ragged)
     if opt is not None:
-      self.step_t.add_(1.0)  # device counter: bias corrections stay right under graph replay
+      if not self._dry_updates:
+        self.step_t.add_(1.0)  # device counter: bias corrections stay right under graph replay
+      kind = _OPT_KIND[opt["kind"]]
+      if self._dry_updates and opt["kind"] == "adam":
+        kind = _OPT_KIND["sgd"]  # a zero gradient would still decay Adam's moments
       ops.segment_update(self.mpdesc, self.tdesc, n_mp, B, B, self.recv_width, self.recv_ptr,
-                         keys, items, seg, n_unique, _OPT_KIND[opt["kind"]], opt["lr"],
-                         opt["eps"], opt["beta1"], opt["beta2"], 1.0, 1.0, de.mp_grad_scale,
+                         keys, items, seg, n_unique, kind, opt["lr"],
+                         opt["eps"], opt["beta1"], opt["beta2"], 1.0, 1.0, gscale,
                          opt["weight_decay"], self.lr_t.data_ptr(), None, None, self.max_width,
                          self.act, self.vec4, self._balanced_scratch(), self.step_t.data_ptr())
       if multi:

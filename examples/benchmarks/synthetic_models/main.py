@@ -47,6 +47,9 @@ def main():
   p.add_argument("--row_scale", type=float, default=1.0, help="shrink tables (smoke runs)")
   p.add_argument("--device", default=None)
   p.add_argument("--cuda_graph", type=int, default=1, help="capture the whole step in a CUDA graph")
+  p.add_argument("--trainer", default="auto", choices=["auto", "fast", "autograd"],
+                 help="fast = hand-scheduled static step (SyntheticTrainStep); autograd = "
+                 "nn.Module + HybridTrainer; auto = fast when the model / back end allow it")
   args = p.parse_args()
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -86,8 +89,18 @@ def main():
 
   if args.embedding_api == "de":
     lr = {"sgd": 0.03, "adagrad": 0.001, "rowwise_adagrad": 0.001, "adam": 0.001}[args.optimizer]
-    trainer = HybridTrainer(model, lr=lr, embedding_optimizer=args.optimizer,
-                            use_cuda_graph=bool(args.cuda_graph) and use_cuda)
+    from distributed_embeddings_b200.models.synthetic_fast import SyntheticTrainStep
+    why = SyntheticTrainStep.unsupported_reason(model) if use_cuda else "needs CUDA"
+    if args.trainer == "fast" and why:
+      raise ValueError(f"--trainer fast: {why}")
+    if args.trainer != "autograd" and not why:
+      trainer = SyntheticTrainStep(model, lr=lr, embedding_optimizer=args.optimizer,
+                                   use_cuda_graph=bool(args.cuda_graph))
+      trainer_kind = "fast"
+    else:
+      trainer = HybridTrainer(model, lr=lr, embedding_optimizer=args.optimizer,
+                              use_cuda_graph=bool(args.cuda_graph) and use_cuda)
+      trainer_kind = "autograd"
     step = lambda num, cat, lab: trainer.step(num, cat, lab)
   else:
     opt = {"sgd": lambda ps: torch.optim.SGD(ps, lr=0.03),
@@ -141,7 +154,9 @@ def main():
     print(f"Iteration time: {ms:.3f} ms")
     print(json.dumps({"model": args.model, "n_gpus": world, "batch_size": args.batch_size,
                       "ms_per_iter": ms, "samples_per_sec": args.batch_size / ms * 1e3,
-                      "optimizer": args.optimizer, **summary(cfg)}))
+                      "optimizer": args.optimizer,
+                      "trainer": trainer_kind if args.embedding_api == "de" else "native",
+                      **summary(cfg)}))
   if world > 1:
     dist.destroy_process_group()
 

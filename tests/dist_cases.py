@@ -460,6 +460,94 @@ def case_dlrm_fast_step(rank, world, device, backend, optimizer="sgd", steps=2, 
     torch.testing.assert_close(torch.from_numpy(b), torch.from_numpy(a), rtol=3e-2, atol=3e-3)
 
 
+def case_synthetic_fast_step(rank, world, device, backend, optimizer="adagrad", model="tiny",
+                             dp_input=False, steps=2, graph=True, **kw):
+  """SyntheticTrainStep (hand-scheduled kernels, CUDA graph) on `world` ranks against a
+  single-process plain-PyTorch oracle on the global batch: tables as dense tensors, index + sum
+  pooling, concat (+ average pooling), nn.functional MLP under bf16 autocast, autograd, dense
+  SGD / Adagrad.  Shares nothing with the framework but the initial weights."""
+  from distributed_embeddings_b200.models.configs import (ModelConfig, expand, scaled,
+                                                          synthetic_models_v3)
+  from distributed_embeddings_b200.models.synthetic import SyntheticModel
+  from distributed_embeddings_b200.models.synthetic_fast import SyntheticTrainStep
+  cfg = scaled(synthetic_models_v3[model], kw.get("row_scale", 2e-4))
+  if kw.get("interact_stride"):
+    cfg = ModelConfig(cfg.name, cfg.embedding_configs, cfg.mlp_sizes, cfg.num_numerical_features,
+                      kw["interact_stride"])
+  tables, imap, hots = expand(cfg)
+  torch.manual_seed(21)
+  net = SyntheticModel(cfg, dp_input=dp_input, device=device, compute_dtype=torch.bfloat16,
+                       backend="fused", column_slice_threshold=kw.get("column_slice_threshold"))
+  de.broadcast_variables(net)
+  lr = 0.05 if optimizer == "sgd" else 0.01
+  w0 = net.embedding.get_weights(all_ranks=True)
+  lins = [m for m in net.mlp if isinstance(m, torch.nn.Linear)]
+  dense0 = [(l.weight.detach().float().clone(), l.bias.detach().float().clone()) for l in lins]
+  step = SyntheticTrainStep(net, lr=lr, embedding_optimizer=optimizer, use_cuda_graph=graph)
+  gb = 64 * world
+  lb = gb // world
+  g = torch.Generator().manual_seed(4)
+  batches = []
+  for _ in range(steps):
+    num = (torch.rand(gb, cfg.num_numerical_features, generator=g) * 2).to(device)
+    ids = [torch.randint(0, tables[t][0], (gb, h), generator=g).to(device)
+           for t, h in zip(imap, hots)]
+    lab = torch.randint(0, 2, (gb, 1), generator=g).float().to(device)
+    batches.append((num, ids, lab))
+  mine = net.embedding.strategy.input_ids_list[rank]
+  losses = []
+  sl = slice(rank * lb, (rank + 1) * lb)
+  for num, ids, lab in batches:
+    cat = [x[sl] for x in ids] if dp_input else [ids[i] for i in mine]
+    loss = step.step(num[sl], cat, lab[sl]).clone()
+    if world > 1:
+      dist.all_reduce(loss)
+    losses.append(float(loss) / world)
+  step.ctx.check_errors()
+  w1 = net.embedding.get_weights(all_ranks=True)
+
+  # ---- oracle
+  tabs = [torch.from_numpy(w).to(device).requires_grad_(True) for w in w0]
+  dense = [(w.clone().requires_grad_(True), b.clone().requires_grad_(True)) for w, b in dense0]
+  acc = [torch.full_like(t, 0.1) for t in tabs]  # Adagrad initial accumulator value
+  in_dim, in_pad = net._in_dim, net._in_pad
+  olosses = []
+  for num, ids, lab in batches:
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+      outs = [tabs[t][x.long()].sum(1) for t, x in zip(imap, ids)]
+      x = torch.cat(outs, dim=1).to(torch.bfloat16)
+      if cfg.interact_stride:
+        from distributed_embeddings_b200.models.synthetic import _interact
+        x = _interact(x.float(), cfg.interact_stride).to(torch.bfloat16)
+      h = torch.cat([x, num.to(torch.bfloat16),
+                     torch.zeros(gb, in_pad, dtype=torch.bfloat16, device=device)], dim=1)
+      for i, (w, b) in enumerate(dense):
+        h = torch.nn.functional.linear(h, w, b)
+        if i < len(dense) - 1:
+          h = torch.relu(h)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(h.float(), lab)
+    olosses.append(float(loss))
+    params = tabs + [t for wb in dense for t in wb]
+    grads = torch.autograd.grad(loss, params)
+    with torch.no_grad():
+      for i, (p, gr) in enumerate(zip(params, grads)):
+        if i < len(tabs) and optimizer == "adagrad":
+          acc[i] += gr * gr
+          p -= lr * gr / (acc[i].sqrt() + 1e-7)
+        else:
+          p -= lr * gr
+  for a, b in zip(losses, olosses):
+    assert abs(a - b) < 2e-2, (losses, olosses)
+  sq_e = sum(float(((torch.from_numpy(w1[t]).to(device) - tabs[t].detach()).double()**2).sum())
+             for t in range(len(tabs)))
+  sq_u = sum(float(((tabs[t].detach() - torch.from_numpy(w0[t]).to(device)).double()**2).sum())
+             for t in range(len(tabs)))
+  rel = (sq_e / max(sq_u, 1e-30))**0.5
+  assert sq_u > 0 and rel < 0.1, f"table update differs from the oracle: rel L2 {rel:.4f}"
+  for l, (w, b) in zip(lins, dense):
+    torch.testing.assert_close(l.weight.detach().float(), w.detach(), rtol=5e-2, atol=5e-3)
+
+
 def case_checkpoint_resharding(rank, world, device, backend, **kw):
   """Weights written under one sharding load under another and give identical outputs; also
   through .npy files (memory mapped) and with use_lock."""

@@ -94,3 +94,21 @@ def test_dlrm_fast_world2_replicated_tables():
          dp_threshold=300 * 128)
 
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("optimizer,dp_input,stride", [("adagrad", False, None), ("sgd", True, None),
+                                                        ("adagrad", True, 4), ("adam", False, None)])
+def test_synthetic_fast_world1(optimizer, dp_input, stride):
+  if optimizer == "adam":
+    pytest.skip("the plain-PyTorch oracle of this case covers sgd / adagrad")
+  launch("case_synthetic_fast_step", world=1, device_type="cuda", backend="fused",
+         optimizer=optimizer, dp_input=dp_input, interact_stride=stride)
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.parametrize("optimizer,dp_input,stride", [("adagrad", False, None), ("sgd", True, 4)])
+def test_synthetic_fast_world2(optimizer, dp_input, stride):
+  launch("case_synthetic_fast_step", world=2, device_type="cuda", backend="fused",
+         optimizer=optimizer, dp_input=dp_input, interact_stride=stride)

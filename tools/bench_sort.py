@@ -53,10 +53,16 @@ def main():
       t_own = timeit(lambda: ops.radix_sort_pairs(keys, items, bits))
       t_clone = timeit(lambda: (keys.clone(), items.clone()))  # the standalone op clones its inputs
       t_torch = timeit(lambda: torch.sort(keys, stable=True))
+      t_own32, t_clone32 = None, 0.0
+      if bits <= 32:
+        k32 = torch.where(keys >= 2**31, keys - 2**32, keys).to(torch.int32)
+        t_own32 = timeit(lambda: ops.radix_sort_pairs32(k32, items, bits))
+        t_clone32 = timeit(lambda: (k32.clone(), items.clone()))
       ks, _ = ops.radix_sort_pairs(keys, items, bits)
       t_heads = timeit(lambda: ops.head_segments(ks))
       t_uniq = timeit(lambda: torch.unique_consecutive(ks, return_counts=True))
       res = {"n": n, "bits": bits, "own_sort_us": round(t_own - t_clone, 1),
+             "own_sort32_us": round(t_own32 - t_clone32, 1) if t_own32 is not None else None,
              "torch_sort_us": round(t_torch, 1), "own_heads_us": round(t_heads, 1),
              "torch_unique_consecutive_us": round(t_uniq, 1),
              "own_sort_GBps": round(n * 32.0 * ((bits + 7) // 8) / (t_own - t_clone) / 1e3, 1)}
