@@ -83,6 +83,10 @@ class DLRMTrainStep:
     self.engine: FusedEngine = self.emb._engine
     self.n_emb = len(model.table_sizes)
     self.dim = model.embedding_dim
+    # gradient all-to-all through local staging + a streaming copy kernel next to the interaction
+    # backward (DE_B200_STREAM_PUSH=0: the interaction backward stores into peer memory itself)
+    self._stream_push = self.world > 1 and os.environ.get("DE_B200_STREAM_PUSH", "1") == "1"
+    self._push_stream = torch.cuda.Stream(device=self.dev) if self._stream_push else None
 
     lins_b = [m for m in model.bottom_mlp.net if isinstance(m, nn.Linear)]
     lins_t = [m for m in model.top_mlp.net if isinstance(m, nn.Linear)]
@@ -214,6 +218,10 @@ class DLRMTrainStep:
   # ------------------------------------------------------------------ buffers
   def _alloc(self, b: int):
     dev, bf = self.dev, torch.bfloat16
+    if self._stream_push:
+      # chunks of >= 1024 samples, at most 16 of them: the last chunk's transfer is the only part
+      # of the exchange that does not overlap the interaction backward
+      self.engine.enable_streamed_push(max(1024, -(-b // 16)))
     self.engine.prepare(b, [1] * self.n_emb, ids64=False)
     self.cat_stage = self.engine.in_flat[:self.n_emb * b].view(self.n_emb, b)
     self.num_in = torch.zeros(b, self.bottom[0].in_f, dtype=torch.float32, device=dev)
@@ -301,14 +309,29 @@ class DLRMTrainStep:
     # receive buffer of the rank that owns the table (slice) - the gradient all-to-all rides on
     # the kernel's epilogue stores - and its tail signals "gradient ready" to the owners
     hb = self.bottom[-1]
-    ops.interact_bwd(hb.y, eng.out, self.n_emb, self.dz, hb.dy, 0, 0, 1.0, eng.routes_all,
-                     len(eng.routes_all_np), eng.sync_grad_signal())
+    pushed = eng.streamed_push
+    if pushed:
+      # pieces of remote owners are staged locally; the copy kernel (own stream, a few blocks)
+      # forwards every finished chunk over NVLink while the interaction backward keeps computing
+      eng.push_counters.zero_()
+      self._push_stream.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(self._push_stream):
+        eng.launch_streamed_push()
+      ops.interact_bwd(hb.y, eng.out, self.n_emb, self.dz, hb.dy, 0, 0, 1.0, eng.routes_stage,
+                       len(eng.routes_stage_np), [], eng.push_counters, eng.push_chunk_rows)
+    else:
+      ops.interact_bwd(hb.y, eng.out, self.n_emb, self.dz, hb.dy, 0, 0, 1.0, eng.routes_all,
+                       len(eng.routes_all_np), eng.sync_grad_signal(), None, 0)
     # embedding exchange + fused table update, overlapped with the bottom MLP backward
     if self._side is not None:
       self._side.wait_stream(torch.cuda.current_stream())
+      if pushed:  # the update's head waits for every rank's copy kernel: ours must be done first
+        self._side.wait_stream(self._push_stream)
       with torch.cuda.stream(self._side):
         eng.backward_inplace()
     else:
+      if pushed:
+        torch.cuda.current_stream().wait_stream(self._push_stream)
       eng.backward_inplace()
     ops.relu_bwd_bias(hb.dy, hb.y, hb.gb)
     for i in range(len(self.bottom) - 1, -1, -1):

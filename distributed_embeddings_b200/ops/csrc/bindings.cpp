@@ -137,21 +137,22 @@ std::vector<int64_t> struct_sizes() {
 void lookup_fwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
                 int64_t dst_batch, int64_t dst_stride, at::IntArrayRef src_ptrs,
                 at::IntArrayRef dst_ptrs, int64_t rot, bool ids64, int64_t act_dtype, bool vec4,
-                at::IntArrayRef sync) {
+                at::IntArrayRef sync, int64_t tile_samples) {
   TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
   c10::cuda::CUDAGuard guard(descs.device());
   de::launch_lookup_fwd(reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
                         static_cast<int>(n_inputs), batch, src_batch, dst_batch, dst_stride,
                         to_peers(src_ptrs), to_peers(dst_ptrs), static_cast<int>(rot), ids64,
                         static_cast<int>(act_dtype), vec4, sm_count(), cur_stream(),
-                        to_sync(sync));
+                        to_sync(sync), static_cast<int>(tile_samples));
   check_launch();
 }
 
 void scatter_add_bwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64_t src_batch,
                      int64_t grad_batch, int64_t grad_stride, at::IntArrayRef src_ptrs,
                      at::IntArrayRef grad_ptrs, int64_t rot, double scale, int64_t scale_ptr,
-                     bool ids64, int64_t act_dtype, bool vec4, bool vec8, at::IntArrayRef sync) {
+                     bool ids64, int64_t act_dtype, bool vec4, bool vec8, at::IntArrayRef sync,
+                     bool staged) {
   TORCH_CHECK(descs.is_cuda(), "descs must live on the GPU");
   c10::cuda::CUDAGuard guard(descs.device());
   de::launch_scatter_add_bwd(reinterpret_cast<const de::InputDesc*>(descs.data_ptr()),
@@ -159,7 +160,7 @@ void scatter_add_bwd(const Tensor& descs, int64_t n_inputs, int64_t batch, int64
                              to_peers(src_ptrs), to_peers(grad_ptrs), static_cast<int>(rot),
                              static_cast<float>(scale), reinterpret_cast<const float*>(scale_ptr),
                              ids64, static_cast<int>(act_dtype), vec4, sm_count(), cur_stream(),
-                             vec8, to_sync(sync));
+                             vec8, to_sync(sync), staged);
   check_launch();
 }
 
@@ -451,9 +452,16 @@ Tensor embedding_lookup_fwd(const Tensor& param, const Tensor& values,
   std::memset(&src, 0, sizeof(src));
   std::memset(&dst, 0, sizeof(dst));
   dst.p[0] = out.data_ptr();
+  // samples per warp tile: ~64 gathered rows per tile, but never fewer samples than one warp
+  // instruction covers (32 / lanes-per-row) - long segments then spread over many warps
+  const int64_t avg_hot = std::max<int64_t>(1, values.numel() / std::max<int64_t>(batch, 1));
+  int64_t lanes_per_row = 1;
+  while (lanes_per_row < (width + 3) / 4 && lanes_per_row < 32) lanes_per_row *= 2;
+  const int64_t ts = std::max<int64_t>(32 / lanes_per_row, std::min<int64_t>(32, 64 / avg_hot));
   de::launch_lookup_fwd(reinterpret_cast<const de::InputDesc*>(dd.data_ptr()), 1, batch, batch,
                         batch, width, src, dst, 0, values.scalar_type() == at::kLong,
-                        out_bf16 ? 1 : 0, width % 4 == 0, sm_count(), cur_stream(), de::no_sync());
+                        out_bf16 ? 1 : 0, width % 4 == 0, sm_count(), cur_stream(), de::no_sync(),
+                        static_cast<int>(std::max<int64_t>(1, ts)));
   check_launch();
   return out;
 }
@@ -645,6 +653,33 @@ void push_grad(const Tensor& routes, int64_t n_routes, const Tensor& src, int64_
   check_launch();
 }
 
+// Streamed push of an owner-major staging buffer (see de_b200.h PushPlan): src / dst pointers and
+// bytes per row for every peer; counters[c] = rows of chunk c the producer has completed.
+void stream_push(at::IntArrayRef src_ptrs, at::IntArrayRef dst_ptrs, at::IntArrayRef row_bytes,
+                 const Tensor& counters, int64_t chunk_rows, int64_t rows, int64_t blocks,
+                 at::IntArrayRef sync) {
+  TORCH_CHECK(src_ptrs.size() == dst_ptrs.size() && src_ptrs.size() == row_bytes.size() &&
+              src_ptrs.size() <= de::kMaxPeers);
+  TORCH_CHECK(counters.is_cuda() && counters.scalar_type() == at::kInt && chunk_rows > 0 &&
+              counters.numel() >= (rows + chunk_rows - 1) / chunk_rows);
+  de::PushPlan plan;
+  std::memset(&plan, 0, sizeof(plan));
+  plan.n = static_cast<int32_t>(src_ptrs.size());
+  for (size_t i = 0; i < src_ptrs.size(); ++i) {
+    TORCH_CHECK(row_bytes[i] % 16 == 0 && src_ptrs[i] % 16 == 0 && dst_ptrs[i] % 16 == 0,
+                "streamed push needs 16-byte aligned rows");
+    plan.src[i] = reinterpret_cast<const void*>(src_ptrs[i]);
+    plan.dst[i] = reinterpret_cast<void*>(dst_ptrs[i]);
+    plan.row_bytes[i] = row_bytes[i];
+  }
+  c10::cuda::CUDAGuard guard(counters.device());
+  de::SyncArgs sa = to_sync(sync);
+  de::launch_stream_push(plan, reinterpret_cast<const uint32_t*>(counters.data_ptr<int>()),
+                         static_cast<int>(chunk_rows), rows, sa.timeout, sa.error_flag,
+                         static_cast<int>(blocks), cur_stream(), sa);
+  check_launch();
+}
+
 // out[i, dst_col + c] = sum_s partial[s, i, src_col + c]; cols = int32 [n, 3] {src, dst, width}
 void rowslice_reduce(const Tensor& partial, int64_t out_ptr, int64_t out_stride,
                      int64_t out_dtype, const Tensor& cols) {
@@ -745,7 +780,8 @@ void interact_fwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, Tensor
 
 void interact_bwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, const Tensor& dz,
                   Tensor dbottom, int64_t demb_ptr, int64_t demb_stride, double emb_grad_scale,
-                  const c10::optional<Tensor>& routes, int64_t n_routes, at::IntArrayRef sync) {
+                  const c10::optional<Tensor>& routes, int64_t n_routes, at::IntArrayRef sync,
+                  const c10::optional<Tensor>& done_counters, int64_t chunk_rows) {
   check_bf16_2d(bottom, "bottom");
   check_bf16_2d(emb, "emb");
   check_bf16_2d(dz, "dz");
@@ -764,7 +800,11 @@ void interact_bwd(const Tensor& bottom, const Tensor& emb, int64_t n_emb, const 
                                     routes.has_value()
                                         ? reinterpret_cast<const de::GradRoute*>(routes->data_ptr())
                                         : nullptr,
-                                    static_cast<int>(n_routes), to_sync(sync));
+                                    static_cast<int>(n_routes), to_sync(sync),
+                                    done_counters.has_value()
+                                        ? reinterpret_cast<uint32_t*>(done_counters->data_ptr<int>())
+                                        : nullptr,
+                                    static_cast<int>(chunk_rows));
   TORCH_CHECK(ok, "unsupported interaction shape (n_emb <= 31, dim in {32,64,128}; routed / "
                   "signalling launches need dim in {64,128} and 16-byte aligned rows)");
   check_launch();
@@ -954,12 +994,12 @@ TORCH_LIBRARY(de_b200, m) {
   m.def(
       "lookup_fwd(Tensor descs, int n_inputs, int batch, int src_batch, int dst_batch, "
       "int dst_stride, int[] src_ptrs, int[] dst_ptrs, int rot, bool ids64, int act_dtype, "
-      "bool vec4, int[] sync) -> ()",
+      "bool vec4, int[] sync, int tile_samples) -> ()",
       &lookup_fwd);
   m.def(
       "scatter_add_bwd(Tensor descs, int n_inputs, int batch, int src_batch, int grad_batch, "
       "int grad_stride, int[] src_ptrs, int[] grad_ptrs, int rot, float scale, int scale_ptr, bool ids64, "
-      "int act_dtype, bool vec4, bool vec8, int[] sync) -> ()",
+      "int act_dtype, bool vec4, bool vec8, int[] sync, bool staged) -> ()",
       &scatter_add_bwd);
   m.def(
       "sort_items(Tensor descs, Tensor tables, int n_tables, int n_inputs, int batch, "
@@ -1021,6 +1061,10 @@ TORCH_LIBRARY(de_b200, m) {
       "-> ()",
       &push_grad);
   m.def(
+      "stream_push(int[] src_ptrs, int[] dst_ptrs, int[] row_bytes, Tensor counters, "
+      "int chunk_rows, int rows, int blocks, int[] sync) -> ()",
+      &stream_push);
+  m.def(
       "rowslice_reduce(Tensor partial, int out_ptr, int out_stride, int out_dtype, Tensor cols) "
       "-> ()",
       &rowslice_reduce);
@@ -1037,7 +1081,7 @@ TORCH_LIBRARY(de_b200, m) {
   m.def(
       "interact_bwd(Tensor bottom, Tensor emb, int n_emb, Tensor dz, Tensor(a!) dbottom, "
       "int demb_ptr, int demb_stride, float emb_grad_scale, Tensor? routes, int n_routes, "
-      "int[] sync) -> ()",
+      "int[] sync, Tensor? done_counters, int chunk_rows) -> ()",
       &interact_bwd);
   m.def("avgpool_fwd(Tensor x, int n, Tensor(a!) out, int stride) -> ()", &avgpool_fwd);
   m.def("avgpool_bwd(Tensor dout, Tensor(a!) dx, int n, int stride) -> ()", &avgpool_bwd);

@@ -342,6 +342,56 @@ push_grad_kernel(const GradRoute* __restrict__ routes, int n_routes, const S* __
   sync_tail(sync);
 }
 
+// ----------------------------------------------------------------------------- streamed push
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(512)
+stream_push_kernel(const __grid_constant__ PushPlan plan, const uint32_t* __restrict__ counters,
+                   int chunk_rows, int64_t rows, unsigned long long timeout, int* error_flag,
+                   const __grid_constant__ SyncArgs sync) {
+  const int64_t n_chunks = (rows + chunk_rows - 1) / chunk_rows;
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t n_thr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int64_t r0 = c * chunk_rows;
+    const int64_t left = rows - r0;
+    const uint32_t nr = static_cast<uint32_t>(left < chunk_rows ? left : chunk_rows);
+    if (threadIdx.x == 0) {
+      // the producer of this GPU counts finished rows per chunk (local memory: cheap to poll)
+      const unsigned long long start = clock64();
+      unsigned spins = 0;
+      while (ld_acquire_gpu_u32(counters + c) < nr) {
+        if ((++spins & 0x3ff) == 0 && timeout && (clock64() - start) > timeout)
+          peer_timeout_trap(error_flag, sync.rank);
+        __nanosleep(100);
+      }
+    }
+    __syncthreads();
+    for (int p = 0; p < plan.n; ++p) {
+      const int64_t n16 = (static_cast<int64_t>(nr) * plan.row_bytes[p]) >> 4;
+      const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const char*>(plan.src[p]) +
+                                                       r0 * plan.row_bytes[p]);
+      uint4* dp = reinterpret_cast<uint4*>(static_cast<char*>(plan.dst[p]) +
+                                           r0 * plan.row_bytes[p]);
+      constexpr int kU = 4;
+      int64_t i = tid;
+      for (; i + (kU - 1) * n_thr < n16; i += kU * n_thr) {
+        uint4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) v[u] = sp[i + u * n_thr];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) dp[i + u * n_thr] = v[u];
+      }
+      for (; i < n16; i += n_thr) dp[i] = sp[i];
+    }
+  }
+  sync_tail(sync);  // every staged row is on its way: "gradient ready" to the owners
+}
+
 // ----------------------------------------------------------------------------- row-slice sum
 // Multi-hot row-sliced inputs: every rank pooled the ids it owns and stored its partial result
 // in slot `rank` of the requester; the requester sums the W slots into its output row (the
@@ -628,6 +678,17 @@ void launch_p2p_store_bench(const void* src, void* dst, int64_t n_rows, int row_
   else
     p2p_store_bench_kernel<uint32_t><<<blocks, threads, 0, stream>>>(s, d, n_rows, row_bytes,
                                                                      dst_stride, unroll);
+}
+
+void launch_stream_push(const PushPlan& plan, const uint32_t* counters, int chunk_rows,
+                        int64_t rows, unsigned long long timeout, int* error_flag, int blocks,
+                        cudaStream_t stream, const SyncArgs& sync) {
+  if (plan.n <= 0 || rows <= 0) {
+    launch_sync_only(sync, stream);
+    return;
+  }
+  stream_push_kernel<<<blocks, 512, 0, stream>>>(plan, counters, chunk_rows, rows, timeout,
+                                                 error_flag, sync);
 }
 
 void launch_sync_only(const SyncArgs& sync, cudaStream_t stream) {

@@ -106,7 +106,8 @@ struct OptimizerArgs {
 void launch_lookup_fwd(const InputDesc* descs, int n_inputs, int64_t batch, int64_t src_batch,
                        int64_t dst_batch, int64_t dst_stride, const PeerPtrs& src,
                        const PeerPtrs& dst, int rot, bool ids64, int act_dtype, bool vec4,
-                       int sm_count, cudaStream_t stream, const SyncArgs& sync);
+                       int sm_count, cudaStream_t stream, const SyncArgs& sync,
+                       int tile_samples = 32);
 
 // ---- backward: atomic scatter-add of (scaled) gradient rows into the table (SGD fast path,
 // also used to build dense gradients of replicated tables). Gradient rows are pulled from
@@ -115,7 +116,8 @@ void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch,
                             int64_t grad_batch, int64_t grad_stride, const PeerPtrs& src,
                             const PeerPtrs& grad, int rot, float scale, const float* scale_ptr,
                             bool ids64, int act_dtype, bool vec4, int sm_count,
-                            cudaStream_t stream, bool vec8, const SyncArgs& sync);
+                            cudaStream_t stream, bool vec8, const SyncArgs& sync,
+                            bool staged = false);
 
 // ---- backward: sorted / deduplicated path -----------------------------------------------
 // keys32: `keys` points at uint32 keys (every key incl. the sentinel fits 32 bits)
@@ -197,6 +199,20 @@ void launch_push_segments(const int64_t* segs, int n_seg, const void* src, const
 void launch_push_grad(const GradRoute* routes, int n_routes, const void* src, int64_t src_stride,
                       int src_dtype, int dst_dtype, int64_t rows, float scale, int sm_count,
                       cudaStream_t stream, const SyncArgs& sync);
+// Streaming push of a locally staged, owner-major gradient buffer: block p of the staging
+// buffer ([rows, row_bytes[p]] contiguous) goes to peer p's receive buffer.  The kernel follows
+// the producer (e.g. the interaction backward) chunk by chunk - it copies chunk c as soon as
+// counters[c] reports all of its rows complete - so the NVLink transfer overlaps the producer's
+// compute instead of blocking its load/store pipe; the tail signals `sync` ("gradient ready").
+struct PushPlan {
+  const void* src[kMaxPeers];
+  void* dst[kMaxPeers];
+  int64_t row_bytes[kMaxPeers];
+  int32_t n;
+};
+void launch_stream_push(const PushPlan& plan, const uint32_t* counters, int chunk_rows,
+                        int64_t rows, unsigned long long timeout, int* error_flag, int blocks,
+                        cudaStream_t stream, const SyncArgs& sync);
 // out[i, dst_col + c] = sum_s partial[s][i, src_col + c]: requester-side sum of the W partial
 // pools of multi-hot row-sliced inputs.  cols[j] = {src_col, dst_col, width}
 void launch_rowslice_reduce(const float* partial, int world, int64_t rows, int64_t part_stride,
@@ -231,7 +247,8 @@ bool launch_interact_bwd(const void* bottom, int64_t bottom_stride, const void* 
                          int64_t dz_stride, void* dbottom, int64_t dbottom_stride, void* demb,
                          int64_t demb_stride, float emb_grad_scale, int64_t batch, int sm_count,
                          cudaStream_t stream, const GradRoute* routes, int n_routes,
-                         const SyncArgs& sync);
+                         const SyncArgs& sync, uint32_t* done_counters = nullptr,
+                         int chunk_rows = 0);
 // 1-D average pooling over bf16 rows ("same" padding; the synthetic models' interaction)
 void launch_avgpool_fwd(const void* x, int64_t x_stride, int n, void* out, int64_t out_stride,
                         int out_len, int stride, int left, int64_t rows, cudaStream_t stream);

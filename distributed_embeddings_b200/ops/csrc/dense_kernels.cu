@@ -302,7 +302,8 @@ interact_bwd_v2_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
                        int64_t dbottom_stride, bf16* __restrict__ demb, int64_t demb_stride,
                        float emb_grad_scale, int64_t batch,
                        const GradRoute* __restrict__ routes, int n_routes,
-                       const __grid_constant__ SyncArgs sync) {
+                       const __grid_constant__ SyncArgs sync, uint32_t* __restrict__ done_counters,
+                       int chunk_rows) {
   constexpr int LD = D + 8;
   constexpr int LDG = 40;
   constexpr int kWarpElems = 2 * kMaxFeat * LD + 2 * kDzMax + kMaxFeat * LDG;
@@ -434,6 +435,11 @@ interact_bwd_v2_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
           *reinterpret_cast<const uint4*>(sF + row * LD + ch * 8);
     }
     __syncwarp();  // all lanes are done with buffer `cur` before the next iteration refills it
+    if (done_counters != nullptr && lane == 0) {
+      // streamed push: tell the copy kernel that this sample's staged rows are complete
+      __threadfence();
+      atomicAdd(done_counters + s / chunk_rows, 1u);
+    }
   }
   cp_async_wait_group<0>();
   sync_tail(sync);  // every gradient piece of this rank is on its way to its owner
@@ -710,7 +716,7 @@ bool launch_interact_bwd(const void* bottom, int64_t bottom_stride, const void* 
                          int64_t dz_stride, void* dbottom, int64_t dbottom_stride, void* demb,
                          int64_t demb_stride, float emb_grad_scale, int64_t batch, int sm_count,
                          cudaStream_t stream, const GradRoute* routes, int n_routes,
-                         const SyncArgs& sync) {
+                         const SyncArgs& sync, uint32_t* done_counters, int chunk_rows) {
   if (n_emb + 1 > kMaxFeat || batch <= 0 || dim % 32 != 0) return false;
   int64_t blocks = (batch + kWarps - 1) / kWarps;
   const int64_t cap = static_cast<int64_t>(sm_count) * 8;
@@ -729,9 +735,9 @@ bool launch_interact_bwd(const void* bottom, int64_t bottom_stride, const void* 
         reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(dbottom)) & 15) == 0 &&
       (dim == 128 || dim == 64) &&
       (routes != nullptr || (demb_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(demb) & 15) == 0));
-  if (routes != nullptr && !v2_ok) return false;  // pieces are pushed by the double-buffered kernel
+  if ((routes != nullptr || done_counters != nullptr) && !v2_ok) return false;  // v2 only
   const bool has_sync = sync.state != nullptr && (sync.wait_ch >= 0 || sync.signal_ch >= 0);
-  if (v2_ok && (!force_v1 || routes != nullptr || has_sync)) {
+  if (v2_ok && (!force_v1 || routes != nullptr || has_sync || done_counters != nullptr)) {
     // two resident blocks per SM, each warp streams its samples through a double buffer
     int64_t blocks2 = (batch + kWarps - 1) / kWarps;
     if (blocks2 > static_cast<int64_t>(sm_count) * 2) blocks2 = static_cast<int64_t>(sm_count) * 2;
@@ -746,7 +752,7 @@ bool launch_interact_bwd(const void* bottom, int64_t bottom_stride, const void* 
         reinterpret_cast<const bf16*>(bottom), bottom_stride, reinterpret_cast<const bf16*>(emb), \
         emb_stride, n_emb, reinterpret_cast<const bf16*>(dz), dz_stride,                         \
         reinterpret_cast<bf16*>(dbottom), dbottom_stride, reinterpret_cast<bf16*>(demb),         \
-        demb_stride, emb_grad_scale, batch, routes, n_routes, sync);                             \
+        demb_stride, emb_grad_scale, batch, routes, n_routes, sync, done_counters, chunk_rows);  \
     return true;                                                                                 \
   }
     if (dim == 128) DE_IBWD2(128)

@@ -40,18 +40,18 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(int64_t t, int n_inputs, int n_dst,
                                                  int64_t tiles_per_dst, int64_t batch,
-                                                 int64_t dst_batch, int rot) {
+                                                 int64_t dst_batch, int rot, int ts = kTile) {
   TileCoord c;
   int dd = static_cast<int>(t % n_dst);
   int64_t rest = t / n_dst;
   c.f = static_cast<int>(rest % n_inputs);
   int64_t chunk = rest / n_inputs;
   c.d = (dd + rot) % n_dst;
-  int64_t local0 = chunk * kTile;
+  int64_t local0 = chunk * ts;
   c.g0 = static_cast<int64_t>(c.d) * dst_batch + local0;
   int64_t lim = min(dst_batch, batch - static_cast<int64_t>(c.d) * dst_batch);
   int64_t rem = lim - local0;
-  c.nsamp = rem < kTile ? static_cast<int>(rem < 0 ? 0 : rem) : kTile;
+  c.nsamp = rem < ts ? static_cast<int>(rem < 0 ? 0 : rem) : ts;
   return c;
 }
 
@@ -98,17 +98,20 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 lookup_fwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
                   int64_t src_batch, int64_t dst_batch, int64_t dst_stride,
                   const __grid_constant__ PeerPtrs src, const __grid_constant__ PeerPtrs dst,
-                  int rot, const __grid_constant__ SyncArgs sync) {
+                  int rot, const __grid_constant__ SyncArgs sync, int ts) {
+  // ts = samples per warp tile (power of two <= 32): 32 for one-hot inputs; multi-hot inputs
+  // get smaller tiles so that a launch still has enough warps when every sample pools tens or
+  // hundreds of rows (the reference splits long reductions over blockDim.y, CU:195-226)
   sync_head(sync);  // the ids of every requester have landed in this rank's id buffer
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
   const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
   const int n_dst = static_cast<int>((batch + dst_batch - 1) / dst_batch);
-  const int64_t tiles_per_dst = (dst_batch + kTile - 1) / kTile;
+  const int64_t tiles_per_dst = (dst_batch + ts - 1) / ts;
   const int64_t total = static_cast<int64_t>(n_inputs) * n_dst * tiles_per_dst;
 
   for (int64_t t = warp; t < total; t += n_warps) {
-    const TileCoord tc = decode_tile(t, n_inputs, n_dst, tiles_per_dst, batch, dst_batch, rot);
+    const TileCoord tc = decode_tile(t, n_inputs, n_dst, tiles_per_dst, batch, dst_batch, rot, ts);
     if (tc.nsamp <= 0) continue;
     const InputDesc D = descs[tc.f];
     const int W = D.width;
@@ -340,6 +343,134 @@ scatter_add_bwd_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_
   sync_tail(sync);  // ids and gradient rows are consumed: the requesters may overwrite them
 }
 
+// ---- staged variant of the atomic SGD update -------------------------------------------------
+// ncu of the kernel above (MLPerf tables, batch 65536): 60 % of the stall samples sit on the
+// unpack right after the gradient-row loads - 4 rows of 8 bytes per lane in flight per warp
+// (~30 KB per SM) do not cover the latency of an L2 that is busy filling lines for the
+// reductions.  Here every warp streams the gradient rows of its *next* tile (32 samples x row
+// bytes, up to 8 KB) into shared memory with cp.async while it reduces the current one from
+// shared memory: no registers held by loads in flight, ~100 KB per SM in flight, the RED
+// instructions issue back to back.  The tile's ids are fetched one tile ahead as well (one
+// coalesced load, lane = sample) and its table rows are prefetched into L2.
+constexpr int kStagedWarps = 7;
+constexpr int kStagedThreads = kStagedWarps * 32;
+constexpr int kStageBytes = 8192;  // one tile: 32 samples x <= 256 bytes of gradient row
+
+__device__ __forceinline__ void cp_async16_g2s(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+
+template <typename IdT, typename GradT>
+__global__ void __launch_bounds__(kStagedThreads, 2)
+scatter_add_staged_kernel(const InputDesc* __restrict__ descs, int n_inputs, int64_t batch,
+                          int64_t src_batch, int64_t grad_batch, int64_t grad_stride,
+                          const __grid_constant__ PeerPtrs src,
+                          const __grid_constant__ PeerPtrs grad, int rot, float scale,
+                          const float* __restrict__ scale_ptr,
+                          const __grid_constant__ SyncArgs sync) {
+  extern __shared__ __align__(16) unsigned char staged_smem[];
+  sync_head(sync);  // every requester's gradient rows have landed in the receive buffer
+  if (scale_ptr != nullptr) scale *= *scale_ptr;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned char* stage = staged_smem + static_cast<size_t>(wib) * 2 * kStageBytes;
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * kStagedWarps + wib;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kStagedWarps;
+  const int n_dst = static_cast<int>((batch + grad_batch - 1) / grad_batch);
+  const int64_t tiles_per_dst = (grad_batch + kTile - 1) / kTile;
+  const int64_t total = static_cast<int64_t>(n_inputs) * n_dst * tiles_per_dst;
+
+  // gradient rows (and, for one-hot inputs, the ids) of tile t -> buffer `buf`
+  auto issue = [&](int64_t t, int buf, long long& ids_out) {
+    const TileCoord tc = decode_tile(t, n_inputs, n_dst, tiles_per_dst, batch, grad_batch, rot);
+    const InputDesc& D = descs[tc.f];
+    const int row_bytes = D.width * static_cast<int>(sizeof(GradT));
+    const int cpr = row_bytes >> 4;  // 16-byte chunks per row
+    const int64_t i0 = tc.g0 - static_cast<int64_t>(tc.d) * grad_batch;
+    const unsigned char* gbase = reinterpret_cast<const unsigned char*>(
+        reinterpret_cast<const GradT*>(grad.p[tc.d]) + i0 * grad_stride + D.dst_col);
+    unsigned char* dst = stage + buf * kStageBytes;
+    const int n_chunks = tc.nsamp * cpr;
+    for (int c = lane; c < n_chunks; c += 32) {
+      const int r = c / cpr, ch = c - r * cpr;
+      cp_async16_g2s(dst + r * row_bytes + (ch << 4),
+                     gbase + static_cast<int64_t>(r) * grad_stride * sizeof(GradT) + (ch << 4));
+    }
+    ids_out = -1;
+    if (D.hotness == 1 && D.offsets == nullptr && lane < tc.nsamp) {
+      const IdReader<IdT> rd = make_reader<IdT>(D, src, src_batch);
+      int n;
+      const IdT* p = rd.sample(tc.g0 + lane, n);
+      ids_out = static_cast<long long>(*p) + D.id_shift;
+      // the row this sample reduces into: have it resident in L2 when the RED arrives
+      if (static_cast<uint64_t>(ids_out) < static_cast<uint64_t>(D.sub_rows)) {
+        const char* row = reinterpret_cast<const char*>(D.table) +
+                          (D.row_base + ids_out) * D.width * 4;
+        for (int l = 0; l < ((D.width * 4 + 127) >> 7); ++l) prefetch_l2(row + (l << 7));
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  long long ids_cur = -1, ids_next = -1;
+  int64_t t = warp;
+  int buf = 0;
+  if (t < total) issue(t, 0, ids_cur);
+  for (; t < total; t += n_warps, buf ^= 1) {
+    const int64_t tn = t + n_warps;
+    if (tn < total) issue(tn, buf ^ 1, ids_next);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    const TileCoord tc = decode_tile(t, n_inputs, n_dst, tiles_per_dst, batch, grad_batch, rot);
+    const InputDesc D = descs[tc.f];
+    const int W = D.width;
+    const int nvec = W >> 2;                        // 4 columns per lane
+    const int lpr = min(32, pow2_ceil(nvec));
+    const int rpw = 32 / lpr;
+    const int sub = lane / lpr, li = lane - sub * lpr;
+    float* table = reinterpret_cast<float*>(const_cast<void*>(D.table));
+    const GradT* srow = reinterpret_cast<const GradT*>(stage + buf * kStageBytes);
+    const bool onehot = (D.hotness == 1) && (D.offsets == nullptr);
+    const IdReader<IdT> rd = make_reader<IdT>(D, src, src_batch);
+    for (int c0 = 0; c0 < nvec; c0 += lpr) {
+      const int cv = c0 + li;
+      const bool col_ok = cv < nvec;
+      const int col = cv << 2;
+      for (int r0 = 0; r0 < tc.nsamp; r0 += rpw) {
+        const int r = r0 + sub;
+        const bool ok = (r < tc.nsamp) && col_ok;
+        if (onehot) {
+          const int64_t id = __shfl_sync(0xffffffffu, ids_cur, r & 31);
+          if (ok && static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows)) {
+            FVec<4> g = ld_act<GradT, 4>(srow + r * W + col);
+            g.scale(scale);
+            red_add_f32<4>(table + (D.row_base + id) * W + col, g);
+          }
+        } else if (ok) {
+          int n;
+          const IdT* p = rd.sample(tc.g0 + r, n);
+          FVec<4> g = ld_act<GradT, 4>(srow + r * W + col);
+          float w = scale;
+          if (D.combiner == 1 && n > 0) w /= static_cast<float>(n);
+          g.scale(w);
+          for (int h = 0; h < n; ++h) {
+            const int64_t id = static_cast<int64_t>(p[h]) + D.id_shift;
+            if (static_cast<uint64_t>(id) < static_cast<uint64_t>(D.sub_rows))
+              red_add_f32<4>(table + (D.row_base + id) * W + col, g);
+          }
+        }
+      }
+    }
+    ids_cur = ids_next;
+    __syncwarp();  // all lanes are done with buffer `buf` before the next iteration refills it
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  sync_tail(sync);  // ids and gradient rows are consumed: the requesters may overwrite them
+}
+
 // DE_B200_EMB_BLOCKS_PER_SM=1..4 caps the resident CTAs per SM of the persistent lookup / scatter
 // grids (default 4 = the launch bound): fewer CTAs leave registers and shared memory for kernels
 // of other streams (the MLP GEMMs overlapped with the embedding exchange).
@@ -360,9 +491,9 @@ int grid_for(int64_t total_tiles, int sm_count, int blocks_per_sm) {
   return static_cast<int>(blocks);
 }
 
-int64_t count_tiles(int n_inputs, int64_t batch, int64_t dst_batch) {
+int64_t count_tiles(int n_inputs, int64_t batch, int64_t dst_batch, int ts = kTile) {
   int64_t n_dst = (batch + dst_batch - 1) / dst_batch;
-  int64_t tiles_per_dst = (dst_batch + kTile - 1) / kTile;
+  int64_t tiles_per_dst = (dst_batch + ts - 1) / ts;
   return static_cast<int64_t>(n_inputs) * n_dst * tiles_per_dst;
 }
 
@@ -370,7 +501,7 @@ int64_t count_tiles(int n_inputs, int64_t batch, int64_t dst_batch) {
 
 #define DE_DISPATCH_FWD(IdT, OutT, VEC)                                                        \
   lookup_fwd_kernel<IdT, OutT, VEC><<<grid, kThreads, 0, stream>>>(                            \
-      descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src, dst, rot, sync)
+      descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src, dst, rot, sync, ts)
 #define DE_DISPATCH_FWD_T(IdT, VEC)                                                            \
   do {                                                                                         \
     if (act_dtype == 1) DE_DISPATCH_FWD(IdT, __nv_bfloat16, VEC);                              \
@@ -381,12 +512,15 @@ int64_t count_tiles(int n_inputs, int64_t batch, int64_t dst_batch) {
 void launch_lookup_fwd(const InputDesc* descs, int n_inputs, int64_t batch, int64_t src_batch,
                        int64_t dst_batch, int64_t dst_stride, const PeerPtrs& src,
                        const PeerPtrs& dst, int rot, bool ids64, int act_dtype, bool vec4,
-                       int sm_count, cudaStream_t stream, const SyncArgs& sync) {
+                       int sm_count, cudaStream_t stream, const SyncArgs& sync,
+                       int tile_samples) {
   if (n_inputs <= 0 || batch <= 0) {
     launch_sync_only(sync, stream);  // keep the signalling protocol in step
     return;
   }
-  const int grid = grid_for(count_tiles(n_inputs, batch, dst_batch), sm_count, kBlocksPerSM);
+  int ts = 1;
+  while (ts * 2 <= tile_samples && ts < kTile) ts *= 2;  // power of two in [1, 32]
+  const int grid = grid_for(count_tiles(n_inputs, batch, dst_batch, ts), sm_count, kBlocksPerSM);
   if (vec4) {
     if (ids64) DE_DISPATCH_FWD_T(int64_t, 4);
     else DE_DISPATCH_FWD_T(int32_t, 4);
@@ -411,9 +545,35 @@ void launch_scatter_add_bwd(const InputDesc* descs, int n_inputs, int64_t batch,
                             int64_t grad_batch, int64_t grad_stride, const PeerPtrs& src,
                             const PeerPtrs& grad, int rot, float scale, const float* scale_ptr,
                             bool ids64, int act_dtype, bool vec4, int sm_count,
-                            cudaStream_t stream, bool vec8, const SyncArgs& sync) {
+                            cudaStream_t stream, bool vec8, const SyncArgs& sync, bool staged) {
   if (n_inputs <= 0 || batch <= 0) {
     launch_sync_only(sync, stream);
+    return;
+  }
+  if (staged && vec4) {
+    // caller guarantees: every gradient row is a 16-byte multiple of at most 256 bytes, 16-byte
+    // aligned in the source (column offsets, row stride, base pointers)
+    const int64_t tiles = count_tiles(n_inputs, batch, grad_batch);
+    int64_t blocks = (tiles + kStagedWarps - 1) / kStagedWarps;
+    if (blocks > static_cast<int64_t>(sm_count) * 2) blocks = static_cast<int64_t>(sm_count) * 2;
+    const size_t smem = static_cast<size_t>(kStagedWarps) * 2 * kStageBytes;
+#define DE_STAGED(IdT, GradT)                                                                     \
+  {                                                                                               \
+    cudaFuncSetAttribute(scatter_add_staged_kernel<IdT, GradT>,                                   \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));    \
+    scatter_add_staged_kernel<IdT, GradT><<<static_cast<unsigned>(blocks), kStagedThreads, smem,  \
+                                           stream>>>(descs, n_inputs, batch, src_batch,           \
+                                                     grad_batch, grad_stride, src, grad, rot,     \
+                                                     scale, scale_ptr, sync);                     \
+  }
+    if (act_dtype == 1) {
+      if (ids64) DE_STAGED(int64_t, __nv_bfloat16) else DE_STAGED(int32_t, __nv_bfloat16)
+    } else if (act_dtype == 2) {
+      if (ids64) DE_STAGED(int64_t, __half) else DE_STAGED(int32_t, __half)
+    } else {
+      if (ids64) DE_STAGED(int64_t, float) else DE_STAGED(int32_t, float)
+    }
+#undef DE_STAGED
     return;
   }
   const int grid = grid_for(count_tiles(n_inputs, batch, grad_batch), sm_count, kBlocksPerSM);

@@ -253,8 +253,9 @@ class DryOps:
 
   # -- forward -------------------------------------------------------------------------------
   def lookup_fwd(self, descs, n_inputs, batch, src_batch, dst_batch, dst_stride, src_ptrs,
-                 dst_ptrs, rot, ids64, act_dtype, vec4, sync):
+                 dst_ptrs, rot, ids64, act_dtype, vec4, sync, tile_samples=32):
     self._count("lookup_fwd")
+    assert 1 <= tile_samples <= 32
     self._wait(sync)
     odt = self._ADT[int(act_dtype)]
     osz = 4 if int(act_dtype) == 0 else 2
@@ -378,9 +379,16 @@ class DryOps:
     return torch.as_strided(g, (ns, width), (grad_stride, 1), col).float()
 
   def scatter_add_bwd(self, descs, n_inputs, batch, src_batch, grad_batch, grad_stride, src_ptrs,
-                      grad_ptrs, rot, scale, scale_ptr, ids64, act_dtype, vec4, vec8, sync):
+                      grad_ptrs, rot, scale, scale_ptr, ids64, act_dtype, vec4, vec8, sync,
+                      staged=False):
     self._count("scatter_add_bwd")
     self._wait(sync)
+    if staged:  # the contract of the cp.async variant: 16-byte multiples / alignment everywhere
+      esz = 4 if int(act_dtype) == 0 else 2
+      assert (grad_stride * esz) % 16 == 0 and all(int(p) % 16 == 0 for p in grad_ptrs)
+      for d in self._descs(descs, n_inputs):
+        rb = int(d["width"]) * esz
+        assert rb % 16 == 0 and rb <= 256 and (int(d["dst_col"]) * esz) % 16 == 0
     if scale_ptr:
       scale = scale * float(self.world.tensor(int(scale_ptr), torch.float32, 1, "lr")[0])
     for d in self._descs(descs, n_inputs):

@@ -36,7 +36,7 @@ def test_interaction_fwd_bwd(n_emb, dim):
   dbottom = torch.empty(b, dim, device="cuda", dtype=torch.bfloat16)
   demb = torch.empty(b, n_emb * dim + 16, device="cuda", dtype=torch.bfloat16)
   ops.interact_bwd(bottom, emb, n_emb, dz, dbottom, demb.data_ptr(), demb.stride(0), 1.0, None, 0,
-                   [])
+                   [], None, 0)
   torch.testing.assert_close(dbottom.float(), bf.grad, rtol=3e-2, atol=3e-2)
   torch.testing.assert_close(demb[:, :n_emb * dim].float(), ef.grad, rtol=3e-2, atol=3e-2)
 
@@ -60,7 +60,7 @@ def test_interaction_bwd_double_buffered(n_emb, dim, b):
   dbottom = torch.empty(b, dim, device="cuda", dtype=torch.bfloat16)
   demb = torch.empty(b, n_emb * dim + 16, device="cuda", dtype=torch.bfloat16)
   ops.interact_bwd(bottom, emb, n_emb, dz, dbottom, demb.data_ptr(), demb.stride(0), 1.0, None, 0,
-                   [])
+                   [], None, 0)
   torch.cuda.synchronize()
   torch.testing.assert_close(dbottom.float(), bf.grad, rtol=3e-2, atol=3e-2)
   torch.testing.assert_close(demb[:, :n_emb * dim].float(), ef.grad, rtol=3e-2, atol=3e-2)
@@ -96,7 +96,7 @@ def test_interaction_bwd_routed():
     routes[i]["src_col"], routes[i]["width"], routes[i]["dst_col"] = sc, w, dc
   dbottom = torch.empty(b, dim, device="cuda", dtype=torch.bfloat16)
   ops.interact_bwd(bottom, emb, n_emb, dz, dbottom, 0, 0, 0.5, upload_struct_array(routes, "cuda"),
-                   len(pieces), [])
+                   len(pieces), [], None, 0)
   torch.cuda.synchronize()
   torch.testing.assert_close(dbottom.float(), bf.grad, rtol=3e-2, atol=3e-2)
   for sc, w, dst, dc in pieces:
