@@ -25,6 +25,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# more hardware queues than the default 8: the step overlaps kernels of ~6 streams (must be set
+# before the CUDA context exists; the package sets the same default on import)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 BASELINE_SAMPLES_PER_SEC = 10416232.0  # 8xA100 AMP, reference examples/dlrm/README.md:8
 

@@ -7,6 +7,13 @@ Public API (capability parity with ``distributed_embeddings/__init__.py:17-27`` 
 ``dist_model_parallel`` is importable as a namespace (``from distributed_embeddings_b200 import
 dist_model_parallel as dmp``).
 """
+import os as _os
+
+# The step overlaps kernels of several streams (embedding exchange, MLP GEMMs, streamed gradient
+# push, all-reduce); with the default of 8 hardware queues distinct streams alias onto one queue
+# and serialise.  Only effective when set before the CUDA context is created.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from .version import __version__
 from .layers.embedding import ConcatOneHotEmbedding, Embedding, IntegerLookup
 from .ops.embedding_lookup_ops import (embedding_lookup, integer_lookup, read_var_no_copy,

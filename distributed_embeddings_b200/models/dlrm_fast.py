@@ -87,6 +87,7 @@ class DLRMTrainStep:
     # backward (DE_B200_STREAM_PUSH=0: the interaction backward stores into peer memory itself)
     self._stream_push = self.world > 1 and os.environ.get("DE_B200_STREAM_PUSH", "1") == "1"
     self._push_stream = torch.cuda.Stream(device=self.dev) if self._stream_push else None
+    self._push_ready = torch.cuda.Event() if self._stream_push else None
 
     lins_b = [m for m in model.bottom_mlp.net if isinstance(m, nn.Linear)]
     lins_t = [m for m in model.top_mlp.net if isinstance(m, nn.Linear)]
@@ -312,13 +313,18 @@ class DLRMTrainStep:
     pushed = eng.streamed_push
     if pushed:
       # pieces of remote owners are staged locally; the copy kernel (own stream, a few blocks)
-      # forwards every finished chunk over NVLink while the interaction backward keeps computing
+      # forwards every finished chunk over NVLink while the interaction backward keeps computing.
+      # The producer is launched FIRST: the copy kernel spins on the producer's progress, so it
+      # must never sit in front of it in a hardware queue the two streams happen to share
+      # (streams alias onto CUDA_DEVICE_MAX_CONNECTIONS queues) - launched second it at worst
+      # runs after the producer instead of next to it.
       eng.push_counters.zero_()
-      self._push_stream.wait_stream(torch.cuda.current_stream())
-      with torch.cuda.stream(self._push_stream):
-        eng.launch_streamed_push()
+      self._push_ready.record(torch.cuda.current_stream())
       ops.interact_bwd(hb.y, eng.out, self.n_emb, self.dz, hb.dy, 0, 0, 1.0, eng.routes_stage,
                        len(eng.routes_stage_np), [], eng.push_counters, eng.push_chunk_rows)
+      self._push_stream.wait_event(self._push_ready)
+      with torch.cuda.stream(self._push_stream):
+        eng.launch_streamed_push()
     else:
       ops.interact_bwd(hb.y, eng.out, self.n_emb, self.dz, hb.dy, 0, 0, 1.0, eng.routes_all,
                        len(eng.routes_all_np), eng.sync_grad_signal(), None, 0)
