@@ -51,9 +51,12 @@ def parse_args():
                  help="elements, 'none', or 'auto' (default) = balance the looked-up columns per "
                  "rank with slices >= 64 wide: 2^32 at 8 GPUs, no slicing at 1-4 (measured "
                  "0.657 vs 0.662 ms at 8 GPUs)")
-  p.add_argument("--data-parallel-threshold", type=int, default=None,
-                 help="replicate tables with at most this many elements (experimental in the fast "
-                 "trainer: e.g. 300000 replicates the 11 tiny MLPerf tables)")
+  p.add_argument("--data-parallel-threshold", default="auto",
+                 help="replicate tables with at most this many elements (the reference's "
+                 "data_parallel_threshold): 'none', a number, or 'auto' (default) = 2500 rows x "
+                 "128 at 2+ GPUs: the 11 MLPerf tables with < 2500 rows hold 0.003 %% of the "
+                 "parameters but 42 %% of the lookups, replicating them takes 42 %% of the bytes "
+                 "off NVLink and their hot rows off a single owner; no effect at 1 GPU")
   p.add_argument("--cuda-graph", type=int, default=1)
   p.add_argument("--gemm", default="cublas", choices=["cublas", "fused_dgrad", "tcgen05", "tcgen05_pair"],
                  help="MLP GEMM path of the fast trainer (see models/dlrm_fast.py)")
@@ -218,8 +221,11 @@ def verify(args, device, world, rank, compute_dtype, cst_for):
   lbv = gbv // world
   torch.manual_seed(4321)
   cst = cst_for(sizes)
+  # same sharding knobs as the timed run, scaled with the rows (replicated tables included)
+  dpt = args.data_parallel_threshold
   model = DLRM(sizes, device=device, compute_dtype=compute_dtype, backend=args.backend,
-               column_slice_threshold=cst, data_parallel_threshold=None)
+               column_slice_threshold=cst,
+               data_parallel_threshold=max(4 * 128, dpt // 1000) if dpt else None)
   from distributed_embeddings_b200 import broadcast_variables
   broadcast_variables(model)
   # oracle copy of the initial state (rank 0 holds the global tables)
@@ -378,6 +384,15 @@ def main():
     cst = None
   else:
     cst = int(cst)
+  dpt = args.data_parallel_threshold
+  if dpt is None or str(dpt).lower() == "none":
+    dpt = None
+  elif str(dpt).lower() == "auto":
+    dpt = 2500 * 128 if (world > 1 and args.optimizer == "sgd" and
+                          args.trainer == "fast" and args.backend == "fused") else None
+  else:
+    dpt = int(dpt)
+  args.data_parallel_threshold = dpt
   verify_result, verify_ok = None, True
   if not args.no_verify:
     raw_cst = args.column_slice_threshold
@@ -442,10 +457,19 @@ def main():
   lab_d = torch.empty(lb, 1, device=device)
   dev_pool = [(n.to(device), c.to(device), l.to(device)) for n, c, l in pool]
 
+  dev_i = [0]
+
   def step_from_device(i):
-    n, c, l = dev_pool[i % len(dev_pool)]
     if use_fast:
-      return trainer.step(n, c, l)
+      # device-resident batches go through the same double-buffered input pipeline as the end
+      # to end loop (copies on the copy stream, one select kernel inside the captured step)
+      if dev_i[0] == 0:
+        trainer.prefetch(*dev_pool[0])
+      loss = trainer.run_prefetched()
+      dev_i[0] += 1
+      trainer.prefetch(*dev_pool[dev_i[0] % len(dev_pool)])
+      return loss
+    n, c, l = dev_pool[i % len(dev_pool)]
     if fused:
       cat_stage.copy_(c)
       return trainer.step(n, None, l, staged=True)
@@ -606,7 +630,7 @@ def main():
             "global_batch": gb,
             "seq_len": 1,
             "parallelism": f"hybrid: dp{world} dense + table-parallel embeddings "
-                           f"(memory_balanced, column_slice_threshold={cst}), backend={args.backend}, trainer={args.trainer}, cuda_graph={int(bool(args.cuda_graph))}, mlp_gemm={args.gemm}, dense_allreduce={getattr(trainer, 'allreduce_kind', 'torch')}",
+                           f"(memory_balanced, column_slice_threshold={cst}, data_parallel_threshold={args.data_parallel_threshold}), backend={args.backend}, trainer={args.trainer}, cuda_graph={int(bool(args.cuda_graph))}, mlp_gemm={args.gemm}, dense_allreduce={getattr(trainer, 'allreduce_kind', 'torch')}",
             "optimizer": f"{args.optimizer} lr={args.lr}, warm-up 8000 / decay from 48000 steps "
                          "like the reference (embedding update fused in backward)",
             "l2_policy": "inputs larger than L2: random rows of "

@@ -159,6 +159,7 @@ class DLRMTrainStep:
       self.p16.copy_(self.p32)
       self._refresh_transposes()
     self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+    self.engine.lr_t = self.lr_t  # dense SGD and the fused embedding update read the same word
     self.lr = float(lr)
     self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
     self._batch = None
@@ -175,10 +176,14 @@ class DLRMTrainStep:
     # backward is done) are all-reduced on a third stream while the interaction backward, the
     # embedding exchange and the bottom MLP backward run; only the small bottom-MLP bucket is
     # reduced at the end.  The overlapped kernel is capped at 32 blocks so that its flag spins
-    # cannot starve the kernels the peers wait for.  DE_B200_AR_OVERLAP=0 restores one all-reduce
-    # at the end of the step.
-    self._ar_stream = torch.cuda.Stream(device=dev) if (
-        overlap and self.world > 1 and os.environ.get("DE_B200_AR_OVERLAP", "1") == "1") else None
+    # cannot starve the kernels the peers wait for.  DE_B200_AR_OVERLAP=0/1 overrides the default
+    # (on from 4 GPUs).
+    ar_env = os.environ.get("DE_B200_AR_OVERLAP", "auto")
+    # measured: +1 % at 8 GPUs, -4 % at 2 GPUs (there the large local batch keeps every SM busy
+    # and the overlapped kernel only steals from the interaction backward)
+    ar_on = ar_env == "1" or (ar_env == "auto" and self.world >= 4)
+    self._ar_stream = torch.cuda.Stream(device=dev) if (overlap and self.world > 1 and ar_on) \
+        else None
 
   def _refresh_transposes(self):
     """K-major copies of W^T for the dgrad GEMMs (2.4 M elements, a few microseconds)."""
@@ -376,8 +381,9 @@ class DLRMTrainStep:
 
   def set_lr(self, lr: float):
     self.lr = float(lr)
-    self.lr_t.fill_(self.lr)
-    self.engine.update_lr(self.lr)
+    self.lr_t.fill_(self.lr)  # shared with the embedding engine: one fill per schedule step
+    if self.emb._fused_optimizer is not None:
+      self.emb._fused_optimizer["lr"] = self.lr
 
   def load_batch(self, numerical, categorical, labels):
     """Copy one batch into the static input buffers (host pinned or device tensors).
@@ -439,7 +445,6 @@ class DLRMTrainStep:
       # warm up on a side stream (cuBLAS handles / workspaces), then capture.  The learning rate
       # is zero while warming up so the extra passes leave the weights untouched.
       self.lr_t.zero_()
-      self.engine.update_lr(0.0)
       self.engine.dry_updates(True)  # optimizer state (Adagrad / Adam) stays untouched as well
       s = torch.cuda.Stream(device=self.dev)
       s.wait_stream(torch.cuda.current_stream())
