@@ -176,14 +176,20 @@ def table_sizes_for(model: str):
   raise ValueError(model)
 
 
-def auto_column_slice_threshold(sizes, dim, world):
+def auto_column_slice_threshold(sizes, dim, world, data_parallel_threshold=None):
   """Pick the column-slice threshold that minimises the most loaded rank's looked-up columns
-  (gather bytes and NVLink bytes per sample are proportional to it); slices stay >= 64 wide."""
+  (gather bytes and NVLink bytes per sample are proportional to it); slices stay >= 64 wide.
+  Replicated tables (``data_parallel_threshold``) do not take part in the exchange."""
   from distributed_embeddings_b200.parallel.strategy import DistEmbeddingStrategy
   cfgs = [{"input_dim": s, "output_dim": dim, "combiner": None} for s in sizes]
   best, best_cols = None, None
   for thr in [None] + [2**k for k in range(34, 22, -1)]:
-    st = DistEmbeddingStrategy(cfgs, world, "memory_balanced", column_slice_threshold=thr)
+    try:
+      st = DistEmbeddingStrategy(cfgs, world, "memory_balanced", column_slice_threshold=thr,
+                                 data_parallel_threshold=data_parallel_threshold
+                                 if world > 1 else None)
+    except ValueError:
+      continue
     if any(not st.local_configs[r] for r in range(world)):
       continue
     if min(c["output_dim"] for r in range(world) for c in st.local_configs[r]) < 64:
@@ -377,13 +383,6 @@ def main():
   gb = args.global_batch
   assert gb % world == 0
   lb = gb // world
-  cst = args.column_slice_threshold
-  if cst == "auto":
-    cst = auto_column_slice_threshold(sizes, 128, world)
-  elif cst is None or str(cst).lower() == "none":
-    cst = None
-  else:
-    cst = int(cst)
   dpt = args.data_parallel_threshold
   if dpt is None or str(dpt).lower() == "none":
     dpt = None
@@ -393,13 +392,21 @@ def main():
   else:
     dpt = int(dpt)
   args.data_parallel_threshold = dpt
+  cst = args.column_slice_threshold
+  if cst == "auto":
+    cst = auto_column_slice_threshold(sizes, 128, world, dpt)
+  elif cst is None or str(cst).lower() == "none":
+    cst = None
+  else:
+    cst = int(cst)
   verify_result, verify_ok = None, True
   if not args.no_verify:
     raw_cst = args.column_slice_threshold
 
     def cst_for(vsizes):
       if raw_cst == "auto":
-        return auto_column_slice_threshold(vsizes, 128, world)
+        return auto_column_slice_threshold(vsizes, 128, world,
+                                           max(4 * 128, dpt // 1000) if dpt else None)
       if raw_cst is None or str(raw_cst).lower() == "none":
         return None
       return max(1, int(raw_cst) // 1000)

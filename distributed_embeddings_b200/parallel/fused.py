@@ -628,6 +628,11 @@ class FusedEngine:
     self.staged_update = os.environ.get("DE_B200_SCATTER_STAGED", "1") == "1" and self.vec4 and \
         len(mp) > 0 and all((w * csz) % 16 == 0 and w * csz <= 256 for w in mpw) and \
         all((c * csz) % 16 == 0 for c in mpc) and (self.recv_width * csz) % 16 == 0
+    # same for the requester-layout gradient of the replicated tables (fast-step path)
+    self.staged_dp = os.environ.get("DE_B200_SCATTER_STAGED", "1") == "1" and self.vec4 and \
+        len(ddesc) > 0 and (tw * csz) % 16 == 0 and \
+        all((int(w) * csz) % 16 == 0 and int(w) * csz <= 256 for w in ddesc["width"]) and \
+        all((int(c) * csz) % 16 == 0 for c in ddesc["dst_col"])
     self._upload()
     self._key = (b, hots, ids64)
 
@@ -954,7 +959,7 @@ class FusedEngine:
     _, dd, n = self._dp_target_desc
     self.ops.scatter_add_bwd(dd, n, self.lb, self.lb, self.lb, self.total_width, [],
                              [self.grad.data_ptr()], 0, 1.0, 0, self.ids64, self.act, self.vec4,
-                             False, [], False)
+                             False, [], self.staged_dp)
 
   @property
   def streamed_push(self) -> bool:

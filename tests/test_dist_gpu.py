@@ -112,3 +112,24 @@ def test_synthetic_fast_world1(optimizer, dp_input, stride):
 def test_synthetic_fast_world2(optimizer, dp_input, stride):
   launch("case_synthetic_fast_step", world=2, device_type="cuda", backend="fused",
          optimizer=optimizer, dp_input=dp_input, interact_stride=stride)
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.parametrize("case", ["case_all_modes", "case_multihot_dp", "case_fuzz"])
+def test_fused_world8(case):
+  """The exchange protocol at the full NVSwitch domain (8 ranks): every sharding mode at once,
+  multi-hot inputs, and randomised plans, against the unsharded model."""
+  if torch.cuda.device_count() < 8:
+    pytest.skip("needs 8 GPUs")
+  kw = {"n_seeds": 6, "seed0": 4000} if case == "case_fuzz" else {}
+  launch(case, world=8, device_type="cuda", backend="fused", timeout=600, **kw)
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+def test_dlrm_fast_world8():
+  if torch.cuda.device_count() < 8:
+    pytest.skip("needs 8 GPUs")
+  launch("case_dlrm_fast_step", world=8, device_type="cuda", backend="fused", optimizer="sgd",
+         dp_threshold=300 * 128, timeout=600)
