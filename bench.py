@@ -54,7 +54,7 @@ def parse_args():
   p.add_argument("--data-parallel-threshold", default="auto",
                  help="replicate tables with at most this many elements (the reference's "
                  "data_parallel_threshold): 'none', a number, or 'auto' (default) = 2500 rows x "
-                 "128 at 4+ GPUs: the 11 MLPerf tables with < 2500 rows hold 0.003 %% of the "
+                 "128 at 2+ GPUs: the 11 MLPerf tables with < 2500 rows hold 0.003 %% of the "
                  "parameters but 42 %% of the lookups, replicating them takes 42 %% of the bytes "
                  "off NVLink and their hot rows off a single owner; no effect at 1 GPU")
   p.add_argument("--cuda-graph", type=int, default=1)
@@ -387,7 +387,7 @@ def main():
   if dpt is None or str(dpt).lower() == "none":
     dpt = None
   elif str(dpt).lower() == "auto":
-    dpt = 2500 * 128 if (world >= 4 and args.optimizer == "sgd" and
+    dpt = 2500 * 128 if (world >= 2 and args.optimizer == "sgd" and
                           args.trainer == "fast" and args.backend == "fused") else None
   else:
     dpt = int(dpt)

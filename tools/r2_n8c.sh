@@ -1,0 +1,31 @@
+#!/bin/bash
+# final 8-GPU batch of round 2: defaults at 8 and 4 GPUs, per-rank timeline at 8, one 8-rank test
+set -u
+O=gpurun_out/r2_n8c; mkdir -p $O
+export DE_B200_FLAG_TIMEOUT_CYCLES=30000000000
+run_bench() {  # n, tag, args...
+  local n=$1 tag=$2; shift 2
+  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
+    --master-port $((29500 + RANDOM % 400)) bench.py --gpus $n "$@" > $O/bench_${tag}_n$n.log 2>&1
+  local rc=$?
+  grep -E '^\{' $O/bench_${tag}_n$n.log | tail -1 > $O/bench_${tag}_n$n.json
+  python - "$O/bench_${tag}_n$n.json" "$tag n=$n rc=$rc" <<'PY' | tee -a $O/summary.txt
+import json, sys
+try:
+  d = json.loads(open(sys.argv[1]).read())
+  v = d.get("verify") or {}
+  print("%-28s ms/step %.4f  %.2f M/s  e2e %s  verify %s (rel_l2 %s / %s)  loss %s" % (
+      sys.argv[2], d.get("ms_per_step", -1), d.get("value", 0) / 1e6,
+      ("%.2f M" % (d["e2e"]["value"] / 1e6)) if d.get("e2e") else None, v.get("ok"),
+      v.get("rel_l2_err_of_update"), v.get("rel_l2_err_vs_autocast_oracle"), d.get("final_loss")))
+except Exception as e:
+  print(sys.argv[2], "no JSON:", e)
+PY
+}
+run_bench 8 fused --steps 50 --warmup 10
+run_bench 8 prof --steps 20 --warmup 5 --no-e2e --no-verify --profile $O/prof_n8.txt --profile-all-ranks --profile-graph 1
+python tools/critical_path.py $O/prof_n8.txt --step 2 > $O/critical_path_n8.txt 2>&1
+rm -f $O/prof_n8.txt*.trace.json
+run_bench 4 fused --steps 50 --warmup 10
+timeout 300 python -m pytest tests/test_dist_gpu.py -m gpu -q -x -p no:cacheprovider -k "dlrm_fast_world8 or (world8 and all_modes)" > $O/pytest_world8.log 2>&1
+echo "pytest world8 rc=$?" | tee -a $O/summary.txt; tail -2 $O/pytest_world8.log | tee -a $O/summary.txt
