@@ -163,7 +163,7 @@ class DLRMTrainStep:
       self.p16.copy_(self.p32)
       self._refresh_transposes()
     self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
-    self.engine.lr_t = self.lr_t  # dense SGD and the fused embedding update read the same word
+    self.engine.share_lr(self.lr_t)  # dense SGD and the fused embedding update read one word
     self.lr = float(lr)
     self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
     self._batch = None

@@ -136,6 +136,7 @@ class FusedEngine:
     self._pending = None   # weakref to the autograd node of the last forward
     self._token = torch.zeros((), device=self.device)
     self.lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)
+    self._lr_external = False  # True once a trainer aliases lr_t with its own device word
     # Adam step count, device resident so that a captured CUDA graph keeps advancing it
     self.step_t = torch.zeros(1, dtype=torch.float32, device=self.device)
     self.opt_state: Dict[int, List[torch.Tensor]] = {}
@@ -697,7 +698,9 @@ class FusedEngine:
       t[m]["state1"] = self._ptr(st[1]) if st and len(st) > 1 else 0
     self.tdesc = _native.upload_struct_array(t, self.device) if len(t) else None
     self._tables_dirty = False
-    if opt is not None:
+    # a trainer that shares its learning-rate word with the engine (DLRMTrainStep) owns it: a
+    # refresh in the middle of its zero-lr graph warm-up must not switch the rate back on
+    if opt is not None and not self._lr_external:
       self.lr_t.fill_(opt["lr"])
 
   # ------------------------------------------------------------------ optimizer state
@@ -726,6 +729,13 @@ class FusedEngine:
 
   def update_lr(self, lr: float):
     self.lr_t.fill_(lr)
+
+  def share_lr(self, lr_t: torch.Tensor):
+    """Use the caller's device-resident learning rate (one word, fp32) for the fused update:
+    a trainer then changes the dense and the embedding rate with a single fill, and the engine
+    never writes it."""
+    self.lr_t = lr_t
+    self._lr_external = True
 
   def step_count(self) -> int:
     """Optimizer steps applied so far (device counter: survives CUDA-graph replays)."""
