@@ -34,7 +34,13 @@ HOT = [
     ("allreduce_multimem_f32", r"allreduce_multimem_kernel<(false|0)>"),
     ("segment_update_bf16_v4", r"segment_update_kernel<__nv_bfloat16, 4>"),
     ("balanced_update_bf16", r"balanced_update_kernel<__nv_bfloat16>"),
-    ("build_keys_i32", r"build_keys_kernel<int>"),
+    ("scatter_add_staged_i32_bf16", r"scatter_add_staged_kernel<int, __nv_bfloat16>"),
+    ("stream_push", r"stream_push_kernel"),
+    ("build_keys_i32_u32", r"build_keys_kernel<int, unsigned int>"),
+    ("digit_hist_u32", r"digit_hist_kernel<unsigned int>"),
+    ("digit_scatter_u32_u32", r"digit_scatter_kernel<unsigned int, unsigned int>"),
+    ("head_compact", r"head_compact_kernel"),
+    ("avgpool_fwd", r"avgpool_fwd_kernel"),
     ("gemm_tn_fused", r"gemm_tn_fused_kernel"),
     ("gemm_tn_pair", r"gemm_tn_pair_kernel"),
     ("integer_lookup", r"integer_lookup_kernel"),
