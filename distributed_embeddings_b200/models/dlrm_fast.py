@@ -104,8 +104,8 @@ class DLRMTrainStep:
     # replicated (data-parallel) embedding tables live in the flat dense buffers too: their
     # local-batch gradient is scattered into the gradient bucket, all-reduced with the MLP
     # gradients and applied by the same fused SGD kernel.  They come first so that they belong to
-    # the bucket that is reduced last (DE_B200_AR_OVERLAP).  Experimental: written after the
-    # round-1 GPU budget was spent (engine side validated in the plan interpreter).
+    # the bucket that is reduced last (DE_B200_AR_OVERLAP).  Validated on 2 and 8 GPUs
+    # (tests/test_dist_gpu.py: replicated-table cases); bench.py replicates the < 2500-row tables.
     self._dp_slots = []
     pos = 0
     if len(self.emb.dp_layers):

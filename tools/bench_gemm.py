@@ -43,7 +43,7 @@ for (n, k) in [(512, 16), (256, 512), (128, 256), (1024, 480), (1024, 1024), (51
     t = timeit(lambda: ops.gemm_tn_bias_act(x, w, bias, out, True, bn))
     res[f"tcgen05_bn{bn}_us"] = round(t, 1)
     res[f"tcgen05_bn{bn}_tflops"] = round(flops / t / 1e6, 1)
-  if os.environ.get("DE_B200_TEST_EXPERIMENTAL", "0") == "1" and n >= 256:
+  if n >= 256:
     # CTA-pair kernel (cta_group::2), see gemm_tn_pair_kernel
     t = timeit(lambda: ops.gemm_tn_bias_act(x, w, bias, out, True, 512))
     res["tcgen05_pair_us"] = round(t, 1)

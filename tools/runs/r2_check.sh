@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU check: the GPU test-suite at the visible world size, then the headline bench and the
 # NCCL-collectives baseline (backend=torch, autograd trainer) at 1..N GPUs.
-#   gpurun --gpus N --timeout 1500 -- 'bash tools/r2_check.sh N [quick]'
+#   gpurun --gpus N --timeout 1500 -- 'bash tools/runs/r2_check.sh N [quick]'
 set -u
 N=${1:-1}
 MODE=${2:-full}

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 single-GPU run: headline + verify, synthetic zoo (hand-scheduled vs autograd trainer),
 # sort micro-benchmark, the single-GPU tests touched this round, and an ncu capture of the hot
-# embedding / interaction kernels.   gpurun --timeout 1500 -- 'bash tools/r2_n1.sh'
+# embedding / interaction kernels.   gpurun --timeout 1500 -- 'bash tools/runs/r2_n1.sh'
 set -u
 O=gpurun_out/r2_n1; mkdir -p $O
 export DE_B200_FLAG_TIMEOUT_CYCLES=${DE_B200_FLAG_TIMEOUT_CYCLES:-30000000000}

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 8-GPU run: 1 -> 8 scaling of the headline on one box, A/B of the two overlap switches at
-# N, per-rank graph-replay timeline at N.   gpurun --gpus 8 --timeout 1200 -- 'bash tools/r2_n8.sh 8'
+# N, per-rank graph-replay timeline at N.   gpurun --gpus 8 --timeout 1200 -- 'bash tools/runs/r2_n8.sh 8'
 set -u
 N=${1:-8}
 O=gpurun_out/r2_n$N; mkdir -p $O

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU run: NVLink store probe, headline at N=2 (all-reduce overlap on / off), 2-rank tests of
-# the hand-scheduled synthetic step.   gpurun --gpus 2 --timeout 900 -- 'bash tools/r2_p2p.sh'
+# the hand-scheduled synthetic step.   gpurun --gpus 2 --timeout 900 -- 'bash tools/runs/r2_p2p.sh'
 set -u
 O=gpurun_out/r2_p2p; mkdir -p $O
 export DE_B200_FLAG_TIMEOUT_CYCLES=${DE_B200_FLAG_TIMEOUT_CYCLES:-30000000000}

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 scaling run on N GPUs: headline at 1..N, per-rank graph-replay timeline at N, A/B of the
 # all-reduce overlap, NCCL-collectives baseline, and the multi-GPU tests that were gated in round 1.
-#   gpurun --gpus N --timeout 1500 -- 'bash tools/r2_scale.sh N [tests]'
+#   gpurun --gpus N --timeout 1500 -- 'bash tools/runs/r2_scale.sh N [tests]'
 set -u
 N=${1:-2}
 TESTS=${2:-tests}

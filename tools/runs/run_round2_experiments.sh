@@ -1,6 +1,6 @@
 #!/bin/bash
 # One-GPU experiment batch queued at the end of round 1 (no GPU budget was left to run it):
-#   gpurun --timeout 900 -- 'bash tools/run_round2_experiments.sh'
+#   gpurun --timeout 900 -- 'bash tools/runs/run_round2_experiments.sh'
 # Everything lands in gpurun_out/round2/.
 set -u
 O=gpurun_out/round2; mkdir -p $O
