@@ -325,6 +325,24 @@ class DryOps:
       torch.as_strided(out, (rows, w), (stride, 1), dc).copy_(
           (src[:, sc:sc + w].float() * scale).to(ddt))
 
+  def stream_push(self, src_ptrs, dst_ptrs, row_bytes, counters, chunk_rows, rows, blocks, sync):
+    """Copy kernel of the streamed gradient push: the locally staged rows of every remote owner
+    are forwarded to that owner's receive buffer.  The real kernel polls the producer's per-chunk
+    row counters; here the producer has already run, so they must be complete."""
+    self._count("stream_push")
+    assert len(src_ptrs) == len(dst_ptrs) == len(row_bytes) and 0 < blocks
+    n_chunks = -(-int(rows) // int(chunk_rows))
+    assert counters.numel() >= n_chunks, "one progress counter per chunk"
+    for c in range(n_chunks):
+      want = min(int(chunk_rows), int(rows) - c * int(chunk_rows))
+      assert int(counters[c]) == want, f"chunk {c}: {int(counters[c])} of {want} rows produced"
+    for sp, dp, rb in zip(src_ptrs, dst_ptrs, row_bytes):
+      assert rb % 16 == 0 and int(sp) % 16 == 0 and int(dp) % 16 == 0, "16-byte copies"
+      n = int(rows) * int(rb)
+      src = self.world.tensor(int(sp), torch.uint8, n, "streamed push staging")
+      dst = self.world.tensor(int(dp), torch.uint8, n, "streamed push destination")
+      dst.copy_(src)
+
   def rowslice_reduce(self, partial, out_ptr, out_stride, out_dtype, cols):
     self._count("rowslice_reduce")
     odt = self._ADT[int(out_dtype)]

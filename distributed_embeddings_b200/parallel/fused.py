@@ -553,7 +553,7 @@ class FusedEngine:
     # owner-major, and forwarded by a copy kernel; every row must be a 16-byte multiple
     self.gstage, self.push_plan, self.push_counters = None, None, None
     stage_base = {}
-    if self.push_chunk_rows and W > 1 and not self.dry and \
+    if self.push_chunk_rows and W > 1 and \
         all((layouts[r]["width"] * csz) % 16 == 0 for r in range(W)):
       offs, pos = {}, 0
       for r in range(W):
@@ -977,8 +977,10 @@ class FusedEngine:
 
   def launch_streamed_push(self, blocks: int = 32):
     """The copy kernel of the streamed gradient push (see :meth:`enable_streamed_push`): launch
-    it on its own stream *before* the producer; the producer gets ``routes_stage``,
-    ``push_counters`` (zeroed by the caller beforehand) and ``push_chunk_rows``."""
+    it on its own stream right *after* the producer (it spins on the producer's progress, so it
+    must never sit in front of it in a hardware queue the two streams share); the producer gets
+    ``routes_stage``, ``push_counters`` (zeroed by the caller beforehand) and
+    ``push_chunk_rows``."""
     src, dst, row_bytes = self.push_plan
     self.ops.stream_push(src, dst, row_bytes, self.push_counters, self.push_chunk_rows, self.lb,
                          blocks, self._sync(signal=CH_GRAD))

@@ -374,11 +374,14 @@ def test_multi_step_with_batch_size_change(world, kind):
   assert outcomes.count("ok") >= max(1, n - 1), outcomes
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
-def test_backward_inplace_with_replicated_tables(world):
+@pytest.mark.parametrize("world,streamed", [(1, False), (2, False), (4, False), (2, True),
+                                            (3, True), (4, True), (5, True), (8, True)])
+def test_backward_inplace_with_replicated_tables(world, streamed):
   """The hand-scheduled step's path: gradient pushed by a fused producer, replicated tables
   accumulate their local-batch dense gradient into persistent targets (later all-reduced with
-  the dense parameters), model-parallel tables are updated in place."""
+  the dense parameters), model-parallel tables are updated in place.  ``streamed``: the
+  producer stages the pieces of remote owners locally (``routes_stage``) and the copy kernel of
+  the streamed push forwards them (the default of the DLRM step from 4 GPUs)."""
   rng = np.random.default_rng(77 + world)
   sizes = [(6, 8), (40, 8), (9, 16), (300, 16), (25, 8), (500, 8)]
   embs = [{"input_dim": r, "output_dim": w, "combiner": None} for r, w in sizes]
@@ -393,8 +396,11 @@ def test_backward_inplace_with_replicated_tables(world):
   dp_tables = des[0].strategy.table_groups[0]
   assert (len(dp_tables) > 0) == (world > 1)
   targets = [[torch.zeros(sizes[t]) for t in dp_tables] for _ in range(world)]
+  chunk = 4  # two chunks per local batch, the second one partial
   for r, de in enumerate(des):
     de._engine.set_dp_grad_targets(targets[r])
+    if streamed:
+      de._engine.enable_streamed_push(chunk)
   ids = [rng.integers(0, r_, size=B) for r_, _ in sizes]
   grads = [rng.standard_normal((B, w)).astype(np.float32) * 0.1 for _, w in sizes]
 
@@ -409,8 +415,16 @@ def test_backward_inplace_with_replicated_tables(world):
       # gradient rows goes through `routes_all` to its owner (replicated inputs: to the local
       # requester-layout buffer), "gradient ready" is signalled from the same launch
       g = torch.from_numpy(np.concatenate([g[sl] for g in grads], 1))
-      eng.ops.push_grad(eng.routes_all, len(eng.routes_all_np), g, eng.act, 1.0,
-                        eng.sync_grad_signal())
+      if streamed:
+        assert eng.streamed_push and len(eng.push_plan[0]) == world - 1
+        eng.push_counters.zero_()
+        eng.ops.push_grad(eng.routes_stage, len(eng.routes_stage_np), g, eng.act, 1.0, [])
+        for c in range(eng.push_counters.numel()):  # the producer's per-chunk progress
+          eng.push_counters[c] = min(chunk, lb - c * chunk)
+        eng.launch_streamed_push()
+      else:
+        eng.ops.push_grad(eng.routes_all, len(eng.routes_all_np), g, eng.act, 1.0,
+                          eng.sync_grad_signal())
       eng.backward_inplace()
 
   dry_run.run_ranks(sim, rank_fn)
