@@ -563,3 +563,109 @@ def test_optimizer_state_resharding(kind):
   resumed = gather(sim_c, des_c, lambda de: de.get_weights())
   for a, b in zip(straight, resumed):
     np.testing.assert_allclose(b, a, rtol=2e-5, atol=2e-6)
+
+
+def test_second_forward_before_backward_takes_the_torch_path():
+  """Two forwards of one layer before any backward (two-tower models, gradient accumulation):
+  the first owns the engine's buffers, the second runs on the torch back end; neither output nor
+  gradient of the first call is disturbed (the reference layer can be called any number of
+  times)."""
+  rng = np.random.default_rng(11)
+  sizes = [(30, 8), (12, 16), (50, 8)]
+  embs = [{"input_dim": r, "output_dim": w, "combiner": None} for r, w in sizes]
+  sim, des = dry_run.build_engines(embs, 1)
+  de = des[0]
+  tables = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+  de.set_weights(tables)
+  b = 5
+  ids1 = [rng.integers(0, r, size=b) for r, _ in sizes]
+  ids2 = [rng.integers(0, r, size=b) for r, _ in sizes]
+  g1 = rng.standard_normal((b, sum(w for _, w in sizes))).astype(np.float32)
+  g2 = rng.standard_normal((b, sum(w for _, w in sizes))).astype(np.float32)
+  seen = {}
+
+  def rank_fn(r):
+    out1 = de([torch.from_numpy(i) for i in ids1], concat=True)
+    assert de._engine.busy()
+    calls = dict(de._engine.ops.calls)
+    out2 = de([torch.from_numpy(i) for i in ids2], concat=True)
+    assert dict(de._engine.ops.calls) == calls, "the second forward must not touch the engine"
+    exp1 = np.concatenate([tables[t][ids1[t]] for t in range(len(sizes))], 1)
+    exp2 = np.concatenate([tables[t][ids2[t]] for t in range(len(sizes))], 1)
+    np.testing.assert_allclose(out1.detach().numpy(), exp1, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(out2.detach().numpy(), exp2, rtol=1e-6, atol=1e-6)
+    (out1 * torch.from_numpy(g1)).sum().backward()
+    assert not de._engine.busy()
+    seen["first"] = assemble(des, _dense_grad)
+    for p in de.parameters():
+      p.grad = None
+    (out2 * torch.from_numpy(g2)).sum().backward()
+    seen["second"] = assemble(des, _dense_grad)
+    out3 = de([torch.from_numpy(i) for i in ids2], concat=True)  # the engine is free again
+    assert dict(de._engine.ops.calls) != calls
+    np.testing.assert_allclose(out3.detach().numpy(), exp2, rtol=1e-6, atol=1e-6)
+
+  dry_run.run_ranks(sim, rank_fn)
+  col = 0
+  for t, (rows, w) in enumerate(sizes):
+    for ids, g, key in ((ids1, g1, "first"), (ids2, g2, "second")):
+      dense = np.zeros((rows, w), dtype=np.float32)
+      np.add.at(dense, ids[t], g[:, col:col + w])
+      np.testing.assert_allclose(seen[key][t], dense, rtol=1e-5, atol=1e-6,
+                                 err_msg=f"{key} backward, table {t}")
+    col += w
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_output_row_stride(world):
+  """``set_out_row_stride``: the lookups of every owner write into a wider requester matrix (the
+  synthetic step's MLP input: embeddings first, other features behind them); the columns behind
+  the embeddings are never touched and the gradient push reads the same strided layout."""
+  rng = np.random.default_rng(21 + world)
+  sizes = [(30, 8), (12, 16), (50, 8), (9, 8)]
+  embs = [{"input_dim": r, "output_dim": w, "combiner": "sum"} for r, w in sizes]
+  sim, des = dry_run.build_engines(embs, world, strategy="memory_balanced")
+  tables = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+  lr, lb, hot = 0.5, 4, 2
+  B = lb * world
+  tw = sum(w for _, w in sizes)
+  stride = tw + 24
+  for de in des:
+    de.set_weights(tables)
+    de.set_optimizer("sgd", lr=lr)
+    de._engine.set_out_row_stride(stride)
+  with pytest.raises(ValueError):
+    des[0]._engine.set_out_row_stride(tw + 4)  # not a multiple of 8
+  with pytest.raises(ValueError):
+    des[0]._engine.set_out_row_stride(tw - 8)  # narrower than the embeddings
+  ids = [rng.integers(0, r, size=(B, hot)) for r, _ in sizes]
+  grads = rng.standard_normal((B, stride)).astype(np.float32) * 0.1
+
+  def rank_fn(r):
+    de, eng = des[r], des[r]._engine
+    sl = slice(r * lb, (r + 1) * lb)
+    with torch.no_grad():
+      eng.stage([torch.from_numpy(i[sl]) for i in ids])
+      eng.out_full[:, tw:] = 7.0  # the consumer's other features
+      eng.launch_forward()
+      eng.wait_output()
+      assert eng.out_full.shape == (lb, stride) and eng.out.shape == (lb, tw)
+      exp = np.concatenate([tables[t][ids[t][sl]].sum(1) for t in range(len(sizes))], 1)
+      np.testing.assert_allclose(eng.out.float().numpy(), exp, rtol=1e-5, atol=1e-5)
+      assert bool((eng.out_full[:, tw:] == 7.0).all())
+      # gradient of the whole strided matrix (a first-layer dgrad): only the embedding columns
+      # are routed to the owners
+      g = torch.from_numpy(grads[sl])
+      eng.ops.push_grad(eng.routes_all, len(eng.routes_all_np), g, eng.act, 1.0,
+                        eng.sync_grad_signal())
+      eng.backward_inplace()
+
+  dry_run.run_ranks(sim, rank_fn)
+  got = assemble(des)
+  col = 0
+  for t, (rows, w) in enumerate(sizes):
+    dense = np.zeros((rows, w), dtype=np.float32)
+    np.add.at(dense, ids[t].reshape(-1), np.repeat(grads[:, col:col + w], hot, axis=0))
+    np.testing.assert_allclose(got[t], tables[t] - lr * dense / world, rtol=1e-5, atol=1e-5,
+                               err_msg=f"table {t}")
+    col += w
