@@ -64,7 +64,7 @@ class DLRMTrainStep:
     # cublas: cuBLASLt everywhere.  fused_dgrad: forward/wgrad on cuBLASLt, dgrad on the
     # first-party tcgen05 kernel with the ReLU-backward mask + bias gradient fused in its epilogue.
     # tcgen05: forward layers on the first-party kernel as well.  tcgen05_pair: same, with the
-    # experimental CTA-pair (cta_group::2) kernel for layers at least 256 wide.
+    # CTA-pair (cta_group::2) kernel for layers at least 256 wide.
     self.gemm = gemm
     self.model = model
     self.emb = model.embedding

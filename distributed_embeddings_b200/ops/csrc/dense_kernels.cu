@@ -255,8 +255,8 @@ interact_bwd_kernel(const bf16* __restrict__ bottom, int64_t bottom_stride,
   }
 }
 
-// ---- v2 of the interaction backward (DE_B200_INTERACT_V2=1; EXPERIMENTAL, written after the
-// round-1 GPU budget was spent).  ncu of v1: 60 % of the issue stalls are long_scoreboard, 25 %
+// ---- v2 of the interaction backward (the default; measured 287 vs 370 us for v1 at one GPU,
+// profiles/r2_experiments/summary.txt).  ncu of v1: 60 % of the issue stalls are long_scoreboard, 25 %
 // warps active - a warp loads a sample, waits, computes, stores, and only then touches the next
 // sample.  v2 keeps the *next* sample's features and dz row in flight (cp.async into a second
 // buffer) while the current one is multiplied and stored, and reads dz from shared memory
