@@ -23,6 +23,7 @@ sanitize:
 sass:
 	$(PYTHON) tools/dump_sass.py
 	$(PYTHON) tools/sass_census.py > profiles/sass_census.txt
+	$(PYTHON) tools/resource_usage.py > profiles/resource_usage.txt
 
 bench:
 	$(PYTHON) bench.py --gpus 1 --steps 50 --warmup 10
