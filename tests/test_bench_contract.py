@@ -58,3 +58,24 @@ def test_auto_column_slice_threshold(world):
   # looked-up columns per rank (what sets gather and NVLink bytes) within 35% of perfect balance
   assert max(cols) <= 1.35 * (26 * 128 / world) + 64
   assert min(c["output_dim"] for r in range(world) for c in st.local_configs[r]) >= 64
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_default_plan_with_replicated_tables(world):
+  """The plan bench.py times by default at N > 1: tables of at most 2500 rows are replicated, the
+  column-slice rule only looks at the tables that are still exchanged."""
+  from distributed_embeddings_b200.parallel.strategy import DistEmbeddingStrategy
+  bench = _load_bench()
+  sizes = bench.table_sizes_for("dlrm-mlperf")
+  dpt = 2500 * 128
+  thr = bench.auto_column_slice_threshold(sizes, 128, world, dpt)
+  cfgs = [{"input_dim": s, "output_dim": 128, "combiner": None} for s in sizes]
+  st = DistEmbeddingStrategy(cfgs, world, "memory_balanced", column_slice_threshold=thr,
+                             data_parallel_threshold=dpt)
+  n_dp = len(st.table_groups[0])
+  assert n_dp == sum(1 for s in sizes if s * 128 <= dpt) == 11
+  assert len(st.table_groups[1]) == 26 - n_dp and not st.table_groups[2]
+  cols = [sum(st.local_configs[r][m]["output_dim"] for m in st.local_maps[r]) for r in range(world)]
+  assert all(c > 0 for c in cols), "every rank owns part of the exchange"
+  mean = (26 - n_dp) * 128 / world
+  assert max(cols) <= max(1.25 * mean, mean + 128), (cols, thr)
