@@ -17,7 +17,8 @@ from collections import defaultdict
 # kernels that wait for peers at their head (flag spins folded into the data kernels)
 WAIT_KERNELS = ("barrier_kernel", "allreduce_p2p_kernel", "allreduce_multimem_kernel",
                 "push_segments_kernel", "lookup_fwd_kernel", "interact_fwd_kernel",
-                "scatter_add_bwd_kernel", "sync_only_kernel")
+                "scatter_add_bwd_kernel", "scatter_add_staged_kernel", "segment_update_kernel",
+                "stream_push_kernel", "sync_only_kernel")
 
 
 def load_kernels(path):
