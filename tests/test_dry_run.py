@@ -669,3 +669,101 @@ def test_output_row_stride(world):
     np.testing.assert_allclose(got[t], tables[t] - lr * dense / world, rtol=1e-5, atol=1e-5,
                                err_msg=f"table {t}")
     col += w
+
+
+def run_inplace_plan(seed, world, streamed):
+  """Random plan for the hand-scheduled steps' backward (``routes_all`` / ``routes_stage`` +
+  ``backward_inplace``): column slices, shared tables, multi-hot sum / mean pooling, replicated
+  tables, one SGD step against the unsharded model."""
+  rng = random.Random(seed)
+  nrng = np.random.default_rng(seed)
+  n_tables = rng.randint(max(2, world // 2), 2 * world + 2)
+  sizes = [(rng.randint(3, 60), rng.choice([4, 8, 12, 16])) for _ in range(n_tables)]
+  hot = rng.choice([1, 1, 2, 3])
+  combiners = [rng.choice(["sum", "mean"]) if hot > 1 else None for _ in sizes]
+  imap = list(range(n_tables)) + [rng.randint(0, n_tables - 1) for _ in range(rng.randint(0, 2))]
+  kw = {"strategy": rng.choice(["basic", "memory_balanced", "memory_optimized"]),
+        "input_table_map": imap}
+  if rng.random() < 0.5:
+    kw["column_slice_threshold"] = rng.choice([60, 150, 300])
+  if world > 1 and rng.random() < 0.6:
+    kw["data_parallel_threshold"] = rng.choice([40, 100])
+  embs = [{"input_dim": r, "output_dim": w, "combiner": c} for (r, w), c in zip(sizes, combiners)]
+  try:
+    sim, des = dry_run.build_engines(embs, world, **kw)
+  except ValueError as e:
+    if "Not enough table" in str(e):
+      return "infeasible"
+    raise
+  tables = [nrng.standard_normal(s).astype(np.float32) for s in sizes]
+  lr = 0.5
+  lb = rng.choice([3, 5, 8])
+  chunk = rng.choice([2, 3, 8])
+  B = lb * world
+  st = des[0].strategy
+  dp_tables = list(st.table_groups[0])
+  targets = [[torch.zeros(sizes[t]) for t in dp_tables] for _ in range(world)]
+  for r, de in enumerate(des):
+    de.set_weights(tables)
+    de.set_optimizer("sgd", lr=lr)
+    de._engine.set_dp_grad_targets(targets[r])
+    if streamed:
+      de._engine.enable_streamed_push(chunk)
+  shape = (B,) if hot == 1 and rng.random() < 0.5 else (B, hot)
+  glob = [nrng.integers(0, sizes[t][0], size=shape) for t in imap]
+  widths = [sizes[t][1] for t in imap]
+  grads = [nrng.standard_normal((B, w)).astype(np.float32) * 0.1 for w in widths]
+
+  def rank_fn(r):
+    de, eng = des[r], des[r]._engine
+    sl = slice(r * lb, (r + 1) * lb)
+    with torch.no_grad():
+      out = de([torch.from_numpy(g[sl]) for g in glob], concat=True)
+      g = torch.from_numpy(np.concatenate([x[sl] for x in grads], 1))
+      if streamed and eng.streamed_push:
+        eng.push_counters.zero_()
+        eng.ops.push_grad(eng.routes_stage, len(eng.routes_stage_np), g, eng.act, 1.0, [])
+        for c in range(eng.push_counters.numel()):
+          eng.push_counters[c] = min(chunk, lb - c * chunk)
+        eng.launch_streamed_push()
+      else:
+        eng.ops.push_grad(eng.routes_all, len(eng.routes_all_np), g, eng.act, 1.0,
+                          eng.sync_grad_signal())
+      eng.backward_inplace()
+      return out.numpy().copy()
+
+  outs = dry_run.run_ranks(sim, rank_fn)
+  ref = [t.copy() for t in tables]
+  ids2d = [g.reshape(B, -1) for g in glob]
+  comb = [c or "sum" for c in combiners]
+  ref_outs = reference_step(ref, imap, ids2d, comb, grads, lr, world, "sgd", {})
+  for r in range(world):
+    exp = np.concatenate([o[r * lb:(r + 1) * lb] for o in ref_outs], 1)
+    np.testing.assert_allclose(outs[r], exp, rtol=1e-4, atol=1e-4, err_msg=f"forward, rank {r}")
+  got = assemble(des)
+  for t in range(n_tables):
+    if t in dp_tables:
+      np.testing.assert_array_equal(got[t], tables[t])
+      j = dp_tables.index(t)
+      for r in range(world):
+        loc = np.zeros_like(tables[t])
+        for i, ti in enumerate(imap):
+          if ti == t:
+            ids = ids2d[i][r * lb:(r + 1) * lb]
+            n = ids.shape[1]
+            g = grads[i][r * lb:(r + 1) * lb] / (n if comb[t] == "mean" else 1)
+            np.add.at(loc, ids.reshape(-1), np.repeat(g, n, axis=0))
+        np.testing.assert_allclose(targets[r][j].numpy(), loc, rtol=1e-4, atol=1e-5,
+                                   err_msg=f"replicated table {t}, rank {r}")
+    else:
+      np.testing.assert_allclose(got[t], ref[t], rtol=1e-3, atol=1e-3, err_msg=f"table {t}")
+  return "ok"
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("streamed", [False, True])
+def test_random_plans_backward_inplace(world, streamed):
+  n = 6 if world < 8 else 3
+  outcomes = [run_inplace_plan(11000 * world + 17 * s + int(streamed), world, streamed)
+              for s in range(n)]
+  assert outcomes.count("ok") >= n // 2 + 1, outcomes
