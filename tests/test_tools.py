@@ -1,0 +1,62 @@
+"""The offline analysis tools keep working on the artifacts committed under profiles/ (no GPU)."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+  return subprocess.run([sys.executable] + list(args), capture_output=True, text=True, cwd=ROOT,
+                        timeout=300, check=False)
+
+
+def test_step_budget_on_the_committed_timeline():
+  out = _run("tools/step_budget.py", "profiles/r2/critical_path_n8.txt")
+  assert out.returncode == 0, out.stderr[-1000:]
+  text = out.stdout
+  assert text.count("== rank ") == 8
+  assert "mean / max over 8 ranks" in text
+  for cat in ("dense GEMM", "embedding lookup", "embedding update", "interaction", "exchange"):
+    assert cat in text
+  # per-rank rows ("   <category>  busy  exposed"): exposed time never exceeds busy time
+  per_rank = text.split("== mean / max")[0]
+  checked = 0
+  for line in per_rank.splitlines():
+    parts = line.split()
+    if line.startswith("   ") and len(parts) >= 3 and not line.strip().startswith("category"):
+      try:
+        busy, exposed = float(parts[-2]), float(parts[-1])
+      except ValueError:
+        continue
+      assert exposed <= busy + 1e-6, line
+      checked += 1
+  assert checked >= 8 * 5
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="CUDA toolkit not on PATH")
+def test_resource_usage_lists_the_hot_kernels():
+  so = os.path.join(ROOT, "distributed_embeddings_b200", "_C.so")
+  if not os.path.exists(so):
+    pytest.skip("extension not built")
+  out = _run("tools/resource_usage.py")
+  assert out.returncode == 0, out.stderr[-1000:]
+  for k in ("lookup_fwd_kernel<int, __nv_bfloat16, 4>", "scatter_add_staged_kernel",
+            "interact_bwd_v2_kernel<128>", "stream_push_kernel", "gemm_tn_pair_kernel",
+            "digit_scatter_kernel", "integer_lookup_kernel"):
+    assert k in out.stdout, k
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="CUDA toolkit not on PATH")
+def test_sass_census_shows_the_blackwell_opcodes():
+  so = os.path.join(ROOT, "distributed_embeddings_b200", "_C.so")
+  if not os.path.exists(so):
+    pytest.skip("extension not built")
+  out = _run("tools/sass_census.py")
+  assert out.returncode == 0, out.stderr[-1000:]
+  text = out.stdout
+  for op in ("UTCHMMA", "UTMALDG", "REDG", "LDGSTS", "HMMA", "STRONG.SYS", "MATCH.ANY"):
+    assert op in text, op
