@@ -28,7 +28,10 @@ sass:
 bench:
 	$(PYTHON) bench.py --gpus 1 --steps 50 --warmup 10
 
+wheel: build
+	$(PYTHON) setup.py -q bdist_wheel -d dist
+
 clean:
 	rm -rf distributed_embeddings_b200/_C.so distributed_embeddings_b200/ops/_build
 
-.PHONY: all build rebuild test test-gpu sanitize sass bench clean
+.PHONY: all build rebuild test test-gpu sanitize sass bench wheel clean
