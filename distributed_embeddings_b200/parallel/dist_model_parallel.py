@@ -16,6 +16,7 @@ reference (``DistributedEmbedding`` :712-1214, hybrid helpers :1217-1329).
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional, Sequence, Union
 
 import numpy as np
@@ -687,7 +688,10 @@ class DistributedEmbedding(nn.Module):
     with torch.no_grad():
       for r0 in range(0, rows, step):
         r1 = min(rows, r0 + step)
-        block = torch.from_numpy(np.ascontiguousarray(arr[r0:r1], dtype=np.float32))
+        host = np.ascontiguousarray(arr[r0:r1], dtype=np.float32)
+        if not host.flags.writeable:  # read-only memory map: torch wants a writable buffer
+          host = host.copy()
+        block = torch.from_numpy(host)
         param[row0 + r0:row0 + r1].copy_(block.to(param.device, non_blocking=False))
 
   def set_weights(self, weights: Sequence[Union[np.ndarray, str, torch.Tensor]],
@@ -737,6 +741,81 @@ class DistributedEmbedding(nn.Module):
     if use_lock and self.world_size > 1:
       for _ in range(self.world_size - self.rank):
         dist.barrier(group=self.group)
+
+  # -- file checkpoints: every rank writes / reads its own slices, no gather -----------------
+  def _barrier(self):
+    if self.world_size > 1:
+      hook = getattr(self, "_barrier_hook", None)  # plan interpreter: ranks are threads
+      if hook is not None:
+        hook()
+      else:
+        dist.barrier(group=self.group)
+
+  @staticmethod
+  def _write_chunked(mm, row0: int, col0: int, src: torch.Tensor, chunk: int):
+    """``mm[row0:row0+rows, col0:col0+width] = src`` in row chunks (one device->host copy of at
+    most ``chunk`` elements at a time)."""
+    rows, width = int(src.shape[0]), int(src.shape[1])
+    step = max(1, chunk // max(1, width))
+    for r0 in range(0, rows, step):
+      r1 = min(rows, r0 + step)
+      mm[row0 + r0:row0 + r1, col0:col0 + width] = \
+          src[r0:r1].detach().to(torch.float32).cpu().numpy()
+
+  def save_weights(self, directory: str, chunk: int = 134217728, prefix: str = "table") -> List[str]:
+    """Write the tables as ``<directory>/<prefix>_<t>.npy`` in the same *global* layout
+    :meth:`get_weights` returns (``[rows, width]`` fp32 per table, original order), without
+    gathering them anywhere: rank 0 creates the files, then **every rank writes its own column /
+    row slices straight into the memory-mapped files in parallel**.  ``directory`` must be
+    visible to all ranks (one host, or a shared file system).  For the 774 GiB synthetic model
+    that is 1/W of the bytes per rank and no collective at all, where :meth:`get_weights`
+    funnels every shard through a broadcast.  The files load with :meth:`load_weights` /
+    :meth:`set_weights` under any sharding.  Collective: every rank must call it; returns the
+    paths."""
+    st = self.strategy
+    n_tables = len(st.global_configs)
+    paths = [os.path.join(directory, f"{prefix}_{t}.npy") for t in range(n_tables)]
+    if self.rank == 0:
+      os.makedirs(directory, exist_ok=True)
+      for t, path in enumerate(paths):
+        cfg = st.global_configs[t]
+        mm = np.lib.format.open_memmap(path, mode="w+", dtype=np.float32,
+                                       shape=(int(cfg["input_dim"]), int(cfg["output_dim"])))
+        del mm
+    self._barrier()  # the files exist with their final size
+    weights = self.weights
+    n_dp, n_col = len(self.dp_layers), len(self.local_embedding_layers)
+    if self.rank == 0:  # replicated tables: identical everywhere
+      for t, w in zip(st.table_groups[0], weights[:n_dp]):
+        mm = np.load(paths[t], mmap_mode="r+")
+        self._write_chunked(mm, 0, 0, w, chunk)
+        mm.flush()
+    col = weights[n_dp:n_dp + n_col]
+    for s in st.shards[self.rank] if st.table_groups[1] else []:
+      t = st.table_groups[1][s.table]
+      mm = np.load(paths[t], mmap_mode="r+")
+      self._write_chunked(mm, 0, s.col_start, col[s.local_table][s.row_offset:s.row_offset + s.rows],
+                          chunk)
+      mm.flush()
+    row = weights[n_dp + n_col:]
+    for gt, t in enumerate(st.table_groups[2]):
+      lo, _ = st.row_ranges[gt][self.rank]
+      mm = np.load(paths[t], mmap_mode="r+")
+      self._write_chunked(mm, lo, 0, row[gt], chunk)
+      mm.flush()
+    self._barrier()  # every slice is on disk
+    return paths
+
+  def load_weights(self, directory: str, chunk: int = 134217728, use_lock: bool = False,
+                   prefix: str = "table"):
+    """Load a checkpoint written by :meth:`save_weights` (any world size / sharding): every rank
+    memory-maps the files and copies only its own slices."""
+    n_tables = len(self.strategy.global_configs)
+    paths = [os.path.join(directory, f"{prefix}_{t}.npy") for t in range(n_tables)]
+    missing = [p for p in paths if not os.path.exists(p)]
+    if missing:
+      raise FileNotFoundError(f"checkpoint is incomplete, missing {missing[:3]}")
+    self.set_weights(paths, chunk=chunk, use_lock=use_lock)
 
   @staticmethod
   def _check_shape(arr, cfg, t):
@@ -800,17 +879,92 @@ class DistributedEmbedding(nn.Module):
           for k, arr in enumerate(tables[t]):
             dst = eng.opt_state[s.local_table][k][s.row_offset:s.row_offset + s.rows]
             src = np.asarray(arr)[:, 0] if per_row else np.asarray(arr)[:, s.col_start:s.col_end]
-            dst.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)))
+            dst.copy_(torch.from_numpy(np.array(src, dtype=np.float32)))
         for gt, t in enumerate(st.table_groups[2]):
           lo, hi = st.row_ranges[gt][self.rank]
           for k, arr in enumerate(tables[t]):
             src = np.asarray(arr)[lo:hi, 0] if per_row else np.asarray(arr)[lo:hi]
-            eng.opt_state[n_col + gt][k].copy_(
-                torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)))
+            eng.opt_state[n_col + gt][k].copy_(torch.from_numpy(np.array(src, dtype=np.float32)))
     step = int(state.get("step", 0))
     eng.step_t.fill_(float(step))
     self._fused_optimizer["step"] = step
     eng._tables_dirty = True
+
+  def save_optimizer_state(self, directory: str, chunk: int = 134217728) -> Optional[str]:
+    """File counterpart of :meth:`get_optimizer_state`: ``optimizer.json`` (kind, step, slots)
+    plus one ``opt_<t>_slot<k>.npy`` per table and state slot in the global layout.  Adagrad /
+    Adam state is element-wise, so every rank writes its own slices in parallel like
+    :meth:`save_weights`; row-wise Adagrad needs the width-weighted mean over a table's column
+    slices and goes through the gather of :meth:`get_optimizer_state` (rank 0 writes).
+    Collective; returns the path of ``optimizer.json`` (None when there is no state)."""
+    import json  # pylint: disable=import-outside-toplevel
+    opt, eng = self._fused_optimizer, self._engine
+    if opt is None or eng is None or not eng.opt_state:
+      return None
+    st = self.strategy
+    kind = opt["kind"]
+    n_slots = len(next(iter(eng.opt_state.values())))
+    n_tables = len(st.global_configs)
+    meta_path = os.path.join(directory, "optimizer.json")
+    has_state = [t not in st.table_groups[0] for t in range(n_tables)]
+
+    def path(t, k):
+      return os.path.join(directory, f"opt_{t}_slot{k}.npy")
+
+    if kind == "rowwise_adagrad":
+      state = self.get_optimizer_state()
+      if self.rank == 0:
+        os.makedirs(directory, exist_ok=True)
+        for t in range(n_tables):
+          if has_state[t]:
+            for k, arr in enumerate(state["tables"][t]):
+              np.save(path(t, k), arr)
+    else:
+      if self.rank == 0:
+        os.makedirs(directory, exist_ok=True)
+        for t in range(n_tables):
+          if has_state[t]:
+            cfg = st.global_configs[t]
+            for k in range(n_slots):
+              mm = np.lib.format.open_memmap(
+                  path(t, k), mode="w+", dtype=np.float32,
+                  shape=(int(cfg["input_dim"]), int(cfg["output_dim"])))
+              del mm
+      self._barrier()
+      n_col = len(self.local_embedding_layers)
+      for s in st.shards[self.rank] if st.table_groups[1] else []:
+        t = st.table_groups[1][s.table]
+        for k in range(n_slots):
+          mm = np.load(path(t, k), mmap_mode="r+")
+          self._write_chunked(mm, 0, s.col_start,
+                              eng.opt_state[s.local_table][k][s.row_offset:s.row_offset + s.rows],
+                              chunk)
+          mm.flush()
+      for gt, t in enumerate(st.table_groups[2]):
+        lo, _ = st.row_ranges[gt][self.rank]
+        for k in range(n_slots):
+          mm = np.load(path(t, k), mmap_mode="r+")
+          self._write_chunked(mm, lo, 0, eng.opt_state[n_col + gt][k], chunk)
+          mm.flush()
+    step = eng.step_count()
+    if self.rank == 0:
+      with open(meta_path, "w", encoding="utf-8") as f:
+        json.dump({"kind": kind, "step": step, "slots": n_slots,
+                   "tables": [bool(x) for x in has_state]}, f)
+    self._barrier()
+    return meta_path
+
+  def load_optimizer_state(self, directory: str):
+    """Load what :meth:`save_optimizer_state` wrote (any world size / sharding); the arrays stay
+    memory mapped, every rank reads only its slices."""
+    import json  # pylint: disable=import-outside-toplevel
+    with open(os.path.join(directory, "optimizer.json"), encoding="utf-8") as f:
+      meta = json.load(f)
+    tables = []
+    for t, has in enumerate(meta["tables"]):
+      tables.append([np.load(os.path.join(directory, f"opt_{t}_slot{k}.npy"), mmap_mode="r")
+                     for k in range(int(meta["slots"]))] if has else None)
+    self.set_optimizer_state({"kind": meta["kind"], "step": int(meta["step"]), "tables": tables})
 
   def close(self):
     """Release the fused engine's peer-mapped buffers (collective over the process group).

@@ -587,6 +587,7 @@ def build_engines(embeddings: Sequence[dict], world_size: int, **kwargs):
                               world_size=world_size, rank=r, **kwargs)
     de.backend = "fused"
     de._bcast_hook = world.bcast
+    de._barrier_hook = world.barrier
     de._engine = _fused.FusedEngine(de, dry=DryRank(world, r))
     des.append(de)
   return world, des

@@ -585,6 +585,42 @@ def case_checkpoint_resharding(rank, world, device, backend, **kw):
   torch.testing.assert_close(oa, ob, rtol=1e-6, atol=1e-6)
 
 
+def case_file_checkpoint(rank, world, device, backend, **kw):
+  """save_weights: concurrent writers (one process per rank) into shared global-layout files,
+  no gather; load_weights under another plan restores the tables bit for bit."""
+  import os
+  import shutil
+  import tempfile
+  sizes = [[300, 8], [40, 16], [1000, 8], [64, 4], [500, 16], [9, 8]]
+  a = EmbeddingListModel(sizes, distribute=True, strategy="memory_balanced", combiner="sum",
+                         column_slice_threshold=1500, device=device, backend=backend)
+  b = EmbeddingListModel(sizes, distribute=True, strategy="basic", combiner="sum",
+                         row_slice_threshold=7000, data_parallel_threshold=100, device=device,
+                         backend=backend)
+  ref = [np.random.RandomState(7 + i).rand(r, w).astype(np.float32) for i, (r, w) in
+         enumerate(sizes)]
+  a.dist_embeddings.set_weights(ref)
+  box = [tempfile.mkdtemp(prefix="de_ckpt_") if rank == 0 else None]
+  if world > 1:
+    dist.broadcast_object_list(box, src=0)
+  ckpt = os.path.join(box[0], "step_1")
+  paths = a.dist_embeddings.save_weights(ckpt, chunk=512)
+  assert len(paths) == len(sizes)
+  for x, path in zip(ref, paths):  # every rank sees complete files after the call returns
+    np.testing.assert_array_equal(np.load(path), x)
+  b.dist_embeddings.load_weights(ckpt, chunk=1024, use_lock=True)
+  for x, y in zip(ref, b.dist_embeddings.get_weights(all_ranks=True)):
+    np.testing.assert_array_equal(x, y)
+  # a second save from the row-sliced / replicated plan overwrites the same files consistently
+  b.dist_embeddings.save_weights(ckpt)
+  for x, path in zip(ref, paths):
+    np.testing.assert_array_equal(np.load(path), x)
+  if world > 1:
+    dist.barrier()
+  if rank == 0:
+    shutil.rmtree(box[0], ignore_errors=True)
+
+
 def case_batch_mismatch(rank, world, device, backend, **kw):
   import pytest
   sizes = [[10, 4], [10, 4]]

@@ -42,3 +42,8 @@ def test_fuzz_plans(world):
 
 def test_independent_subgroups():
   launch("case_subgroups", world=4)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_file_checkpoint_parallel_writers(world):
+  launch("case_file_checkpoint", world=world)

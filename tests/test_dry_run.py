@@ -500,7 +500,7 @@ def test_optimizer_state_checkpoint_resume(kind):
 
 
 @pytest.mark.parametrize("kind", ["adagrad", "adam", "rowwise_adagrad"])
-def test_optimizer_state_resharding(kind):
+def test_optimizer_state_resharding(kind, tmp_path):
   """The global optimizer-state layout is sharding independent: one step on 4 column-sliced
   ranks, state + weights loaded into a 2-rank plan (different slicing, a row-sliced table), a
   second step there == two uninterrupted steps on the 2-rank plan."""
@@ -562,6 +562,31 @@ def test_optimizer_state_resharding(kind):
   step(sim_c, des_c, batches[1])
   resumed = gather(sim_c, des_c, lambda de: de.get_weights())
   for a, b in zip(straight, resumed):
+    np.testing.assert_allclose(b, a, rtol=2e-5, atol=2e-6)
+
+  # the same through files: every rank of the 4-rank job writes its slices (weights and state),
+  # the 2-rank job maps the files and reads its own
+  ckpt = str(tmp_path / "ckpt")
+
+  def save(r):
+    des_b[r].save_weights(ckpt, chunk=64)
+    return des_b[r].save_optimizer_state(ckpt, chunk=64)
+  metas = dry_run.run_ranks(sim_b, save)
+  assert all(m == metas[0] and m.endswith("optimizer.json") for m in metas)
+  for t in range(len(sizes)):
+    for k, arr in enumerate(saved_s["tables"][t]):
+      np.testing.assert_allclose(np.load(f"{ckpt}/opt_{t}_slot{k}.npy"), arr, rtol=1e-6, atol=0)
+  sim_d, des_d = make(2, tables, **kw2)
+
+  def load_files(r):
+    des_d[r]._engine.prepare(gb // 2, [2] * len(sizes))
+    des_d[r].load_weights(ckpt)
+    des_d[r].load_optimizer_state(ckpt)
+  dry_run.run_ranks(sim_d, load_files)
+  assert des_d[0]._engine.step_count() == 1
+  step(sim_d, des_d, batches[1])
+  resumed_files = gather(sim_d, des_d, lambda de: de.get_weights())
+  for a, b in zip(straight, resumed_files):
     np.testing.assert_allclose(b, a, rtol=2e-5, atol=2e-6)
 
 
@@ -767,3 +792,36 @@ def test_random_plans_backward_inplace(world, streamed):
   outcomes = [run_inplace_plan(11000 * world + 17 * s + int(streamed), world, streamed)
               for s in range(n)]
   assert outcomes.count("ok") >= n // 2 + 1, outcomes
+
+
+@pytest.mark.parametrize("world_save,world_load", [(1, 3), (4, 2), (8, 1), (3, 5)])
+def test_file_checkpoint_is_sharding_independent(world_save, world_load, tmp_path):
+  """save_weights: every rank writes its own column / row slices into global-layout .npy files
+  (no gather); load_weights under a different world size and plan restores the same tables."""
+  rng = np.random.default_rng(3)
+  sizes = [(6, 8), (40, 8), (9, 16), (300, 16), (25, 8), (500, 8), (64, 12)]
+  embs = [{"input_dim": r, "output_dim": w, "combiner": "sum"} for r, w in sizes]
+  tables = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+
+  def plan(world, i):
+    kw = {"strategy": ["memory_balanced", "memory_optimized"][i % 2]}
+    if world > 1:
+      kw.update(data_parallel_threshold=100, row_slice_threshold=3500,
+                column_slice_threshold=[1200, 960][i % 2] // world)
+    return dry_run.build_engines(embs, world, **kw)
+
+  sim, des = plan(world_save, 0)
+  for de in des:
+    de.set_weights(tables)
+  ckpt = str(tmp_path / "ckpt")
+  paths = dry_run.run_ranks(sim, lambda r: des[r].save_weights(ckpt, chunk=256))
+  assert all(p == paths[0] for p in paths) and len(paths[0]) == len(sizes)
+  for t, path in enumerate(paths[0]):
+    np.testing.assert_array_equal(np.load(path), tables[t])
+  sim2, des2 = plan(world_load, 1)
+  dry_run.run_ranks(sim2, lambda r: des2[r].load_weights(ckpt, chunk=128))
+  for got, want in zip(assemble(des2), tables):
+    np.testing.assert_array_equal(got, want)
+  os_missing = str(tmp_path / "nothing")
+  with pytest.raises(FileNotFoundError):
+    des2[0].load_weights(os_missing)
