@@ -768,7 +768,7 @@ class DistributedEmbedding(nn.Module):
     gathering them anywhere: rank 0 creates the files, then **every rank writes its own column /
     row slices straight into the memory-mapped files in parallel**.  ``directory`` must be
     visible to all ranks (one host, or a shared file system).  For the 774 GiB synthetic model
-    that is 1/W of the bytes per rank and no collective at all, where :meth:`get_weights`
+    that is 1/W of the bytes per rank and no data collective (two barriers), where :meth:`get_weights`
     funnels every shard through a broadcast.  The files load with :meth:`load_weights` /
     :meth:`set_weights` under any sharding.  Collective: every rank must call it; returns the
     paths."""

@@ -46,6 +46,9 @@ def parse():
   p.add_argument("--fast", action="store_true", help="hand-scheduled step + CUDA graph")
   p.add_argument("--amp", action="store_true", default=True)
   p.add_argument("--save_path", default="/tmp/embedding_weights")
+  p.add_argument("--save_dir", default=None,
+                 help="write one global-layout .npy per table into this directory instead; every "
+                      "rank writes its own slices in parallel (no gather to rank 0)")
   return p.parse_args()
 
 
@@ -137,10 +140,15 @@ def main():
     bce = torch.nn.functional.binary_cross_entropy(p[:n].clamp(1e-7, 1 - 1e-7), y[:n])
     print(f"Evaluation completed, AUC: {auc}, test_loss: {float(bce)}")
 
-  weights = model.embedding.get_weights()
-  if rank == 0:
-    np.savez(args.save_path, *weights)
-    print(f"saved {len(weights)} tables to {args.save_path}.npz")
+  if args.save_dir:
+    paths = model.embedding.save_weights(args.save_dir)
+    if rank == 0:
+      print(f"saved {len(paths)} tables to {args.save_dir}/")
+  else:
+    weights = model.embedding.get_weights()
+    if rank == 0:
+      np.savez(args.save_path, *weights)
+      print(f"saved {len(weights)} tables to {args.save_path}.npz")
   if world > 1:
     dist.destroy_process_group()
 
