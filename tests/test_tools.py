@@ -60,3 +60,22 @@ def test_sass_census_shows_the_blackwell_opcodes():
   text = out.stdout
   for op in ("UTCHMMA", "UTMALDG", "REDG", "LDGSTS", "HMMA", "STRONG.SYS", "MATCH.ANY"):
     assert op in text, op
+
+
+def test_plan_report_cli():
+  import json
+  out = _run("tools/plan_report.py", "--model", "dlrm-mlperf", "--world", "8",
+             "--data-parallel-threshold", "320000", "--json")
+  assert out.returncode == 0, out.stderr[-1000:]
+  rep = json.loads(out.stdout.strip().splitlines()[-1])
+  assert rep["replicated"] == 11 and rep["table_parallel"] == 15 and rep["row_sliced"] == 0
+  assert len(rep["ranks"]) == 8 and all(x["fits"] for x in rep["ranks"])
+  assert max(x["exchanged_columns"] for x in rep["ranks"]) == 256
+  assert 1.0 <= rep["nvlink_imbalance"] < 1.1
+  # human-readable form, a synthetic model with shared multi-hot inputs, explicit tables
+  out = _run("tools/plan_report.py", "--model", "tiny", "--world", "4", "--strategy",
+             "traffic_balanced")
+  assert out.returncode == 0 and "imbalance (max / mean)" in out.stdout, out.stderr[-1000:]
+  out = _run("tools/plan_report.py", "--tables", "1000000x128,5000x64,3000000x32", "--world", "2",
+             "--column-slice-threshold", "auto", "--hbm-gib", "0.1")
+  assert out.returncode == 0 and "GiB!" in out.stdout, out.stdout[-500:] + out.stderr[-500:]
