@@ -102,6 +102,8 @@ class RawBinaryDataset:
     return self._num_entries
 
   def _pinned(self, arr: np.ndarray) -> torch.Tensor:
+    if not arr.flags.writeable:  # np.frombuffer views of the bytes just read are read-only
+      arr = arr.copy()
     t = torch.from_numpy(arr)
     return t.pin_memory() if self._pin else t
 

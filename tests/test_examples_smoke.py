@@ -29,6 +29,23 @@ def test_dlrm_example(tmp_path):
   assert [saved[k].shape for k in saved.files] == [(50, 16), (60, 16), (70, 16)]
 
 
+def test_dlrm_example_on_a_split_binary_dataset(tmp_path):
+  """The real-data path of the DLRM example: split-binary Criteo layout (generated), prefetching
+  reader, training, AUC evaluation, parallel file checkpoint."""
+  data = str(tmp_path / "criteo")
+  run(["tools/make_synthetic_criteo.py", data, "--train", "2048", "--test", "512", "--table_sizes",
+       "5,300,70000,40", "--num_numerical", "13"])
+  ckpt = str(tmp_path / "ckpt")
+  out = run(["examples/dlrm/main.py", "--dataset_path", data, "--batch_size", "256",
+             "--embedding_dim", "16", "--bottom_mlp_dims", "32,16", "--top_mlp_dims", "32,1",
+             "--learning_rate", "1.0", "--save_dir", ckpt])
+  assert "Evaluation completed" in out
+  auc = float(out.split("AUC:")[1].split(",")[0])
+  assert 0.0 <= auc <= 1.0
+  shapes = [np.load(os.path.join(ckpt, f"table_{t}.npy")).shape for t in range(4)]
+  assert shapes == [(5, 16), (300, 16), (70000, 16), (40, 16)]
+
+
 def test_criteo_integer_lookup_example():
   out = run(["examples/criteo/main.py", "--batch_size", "64", "--steps", "2", "--vocab", "100"])
   assert "vocab sizes" in out
