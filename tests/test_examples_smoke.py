@@ -51,6 +51,23 @@ def test_criteo_integer_lookup_example():
   assert "vocab sizes" in out
 
 
+def test_criteo_integer_lookup_example_on_a_text_file(tmp_path):
+  """Criteo text format (tab separated label, 13 counts, 26 hex ids, empty = missing) through
+  IntegerLookup: the vocabulary grows to the number of distinct keys seen (+ the missing key)."""
+  import random
+  rng = random.Random(0)
+  keys = [rng.getrandbits(32) for _ in range(9)]
+  path = str(tmp_path / "train.txt")
+  with open(path, "w", encoding="ascii") as f:
+    for _ in range(200):
+      nums = [str(rng.randint(0, 500)) if rng.random() > 0.2 else "" for _ in range(13)]
+      cats = ["%08x" % rng.choice(keys) if rng.random() > 0.1 else "" for _ in range(26)]
+      f.write("\t".join([str(rng.randint(0, 1))] + nums + cats) + "\n")
+  out = run(["examples/criteo/main.py", "--data", path, "--batch_size", "200", "--vocab", "100",
+             "--epochs", "1"])
+  assert "vocab sizes (first 3 features) [10, 10, 10]" in out, out
+
+
 @pytest.mark.parametrize("api", ["de", "native"])
 def test_synthetic_benchmark_example(api):
   out = run(["examples/benchmarks/synthetic_models/main.py", "--model", "tiny", "--row_scale",
