@@ -23,7 +23,8 @@ from .parallel import dist_model_parallel
 from .parallel.comm import CommContext
 from .parallel.dist_model_parallel import DistributedEmbedding, broadcast_variables
 from .parallel.hybrid import (BroadcastGlobalVariablesCallback, DistributedGradientTape,
-                              DistributedOptimizer, GradBucket, allreduce_gradients)
+                              DistributedOptimizer, GradBucket, allreduce_gradients,
+                              exclude_model_parallel_from_ddp)
 from .parallel.strategy import DistEmbeddingStrategy
 
 # the reference exposes the hybrid helpers through the dist_model_parallel module
@@ -31,11 +32,12 @@ dist_model_parallel.DistributedGradientTape = DistributedGradientTape
 dist_model_parallel.DistributedOptimizer = DistributedOptimizer
 dist_model_parallel.BroadcastGlobalVariablesCallback = BroadcastGlobalVariablesCallback
 dist_model_parallel.allreduce_gradients = allreduce_gradients
+dist_model_parallel.exclude_model_parallel_from_ddp = exclude_model_parallel_from_ddp
 
 __all__ = [
     "Embedding", "IntegerLookup", "ConcatOneHotEmbedding", "embedding_lookup", "integer_lookup",
     "read_var_no_copy", "row_to_split", "RaggedIds", "SparseIds", "DistributedEmbedding",
     "DistEmbeddingStrategy", "broadcast_variables", "DistributedGradientTape",
     "DistributedOptimizer", "BroadcastGlobalVariablesCallback", "GradBucket",
-    "allreduce_gradients", "CommContext", "dist_model_parallel", "__version__"
+    "allreduce_gradients", "exclude_model_parallel_from_ddp", "CommContext", "dist_model_parallel", "__version__"
 ]

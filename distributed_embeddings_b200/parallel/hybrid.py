@@ -12,7 +12,7 @@ NVLink kernel (reduce-scatter + all-gather over peer memory fused with the 1/wor
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional, Sequence
+from typing import Iterable, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -230,6 +230,25 @@ class BroadcastGlobalVariablesCallback:
 
   on_train_begin = __call__
   on_batch_end = __call__
+
+
+def exclude_model_parallel_from_ddp(module: nn.Module) -> List[str]:
+  """Let ``torch.nn.parallel.DistributedDataParallel`` wrap a model that contains a
+  :class:`DistributedEmbedding`: the model-parallel tables (``de_local`` parameters, different on
+  every rank, updated in place or through row-sparse gradients) are put on DDP's ignore list, so
+  DDP neither broadcasts them at construction nor all-reduces their gradients; everything else
+  (replicated tables, MLPs) is handled by DDP as usual.  Call it *before* constructing DDP:
+
+      names = exclude_model_parallel_from_ddp(model)
+      ddp = torch.nn.parallel.DistributedDataParallel(model)
+
+  The PyTorch counterpart of combining the reference layer with Horovod's
+  ``DistributedGradientTape`` (reference dist_model_parallel.py:1241-1290).  Returns the ignored
+  parameter names."""
+  names = [n for n, p in module.named_parameters() if getattr(p, "de_local", False)]
+  from torch.nn.parallel import DistributedDataParallel as DDP  # pylint: disable=import-outside-toplevel
+  DDP._set_params_and_buffers_to_ignore_for_model(module, names)  # pylint: disable=protected-access
+  return names
 
 
 class SparseRowOptimizer:

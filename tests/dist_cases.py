@@ -621,6 +621,51 @@ def case_file_checkpoint(rank, world, device, backend, **kw):
     shutil.rmtree(box[0], ignore_errors=True)
 
 
+def case_ddp_interop(rank, world, device, backend, **kw):
+  """torch DistributedDataParallel around a model with a DistributedEmbedding: model-parallel
+  tables are excluded from DDP (exclude_model_parallel_from_ddp), replicated tables and the dense
+  layer are averaged by DDP; one SGD step equals the undistributed model on the global batch."""
+  from torch.nn.parallel import DistributedDataParallel as DDP
+  torch.manual_seed(60)
+  sizes = [[30, 8], [12, 4], [50, 8], [9, 4], [40, 8]]
+  ref = EmbeddingListModel(sizes, distribute=False, combiner="sum", device=device)
+  test = EmbeddingListModel(sizes, distribute=True, strategy="memory_balanced", combiner="sum",
+                            data_parallel_threshold=60, device=device, backend=backend)
+  for p in ref.parameters():
+    dist.broadcast(p.data, src=0)
+  test.dist_embeddings.set_weights([e.embeddings.detach().cpu().numpy() for e in ref.embeddings])
+  with torch.no_grad():
+    test.dense.weight.copy_(ref.dense.weight)
+    test.dense.bias.copy_(ref.dense.bias)
+  ignored = dmp.exclude_model_parallel_from_ddp(test)
+  n_mp = len(test.dist_embeddings.mp_parameters())
+  assert len(ignored) == n_mp > 0 and len(test.dist_embeddings.dp_layers) > 0
+  dev = torch.device(device)
+  ddp = DDP(test) if dev.type == "cpu" else DDP(test, device_ids=[dev.index])
+  lb, lr = 6, 0.5
+  glob = gen_inputs(61, lb * world, sizes, hotness=2, device=device)
+  inputs = [slice_batch(x, rank, lb) for x in glob]
+  loss = ddp(inputs).square().mean()
+  loss.backward()
+  with torch.no_grad():
+    for p in test.parameters():
+      if p.grad is None:
+        continue
+      g = p.grad.to_dense() if p.grad.is_sparse else p.grad
+      p -= lr * g  # model-parallel gradients already follow the global-mean contract
+  ref_loss = ref(glob).square().mean()
+  grads = torch.autograd.grad(ref_loss, list(ref.parameters()))
+  with torch.no_grad():
+    for p, g in zip(ref.parameters(), grads):
+      p -= lr * (g.to_dense() if g.is_sparse else g)
+  got = test.dist_embeddings.get_weights(all_ranks=True)
+  for e, w in zip(ref.embeddings, got):
+    torch.testing.assert_close(torch.from_numpy(w), e.embeddings.detach().cpu(), rtol=1e-5,
+                               atol=1e-6)
+  torch.testing.assert_close(test.dense.weight, ref.dense.weight, rtol=1e-5, atol=1e-6)
+  torch.testing.assert_close(test.dense.bias, ref.dense.bias, rtol=1e-5, atol=1e-6)
+
+
 def case_batch_mismatch(rank, world, device, backend, **kw):
   import pytest
   sizes = [[10, 4], [10, 4]]

@@ -47,3 +47,8 @@ def test_independent_subgroups():
 @pytest.mark.parametrize("world", [2, 3])
 def test_file_checkpoint_parallel_writers(world):
   launch("case_file_checkpoint", world=world)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ddp_interop(world):
+  launch("case_ddp_interop", world=world)
