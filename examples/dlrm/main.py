@@ -45,6 +45,10 @@ def parse():
   p.add_argument("--dist_strategy", default="memory_balanced")
   p.add_argument("--fast", action="store_true", help="hand-scheduled step + CUDA graph")
   p.add_argument("--amp", action="store_true", default=True)
+  p.add_argument("--warmup_steps", type=int, default=8000)
+  p.add_argument("--decay_start_step", type=int, default=48000)
+  p.add_argument("--decay_steps", type=int, default=24000)
+  p.add_argument("--epochs", type=int, default=1)
   p.add_argument("--save_path", default="/tmp/embedding_weights")
   p.add_argument("--save_dir", default=None,
                  help="write one global-layout .npy per table into this directory instead; every "
@@ -93,8 +97,9 @@ def main():
     evald = DummyDataset(args.batch_size, args.num_numerical_features, world, len(table_ids),
                          False, args.dp_input, max(1, args.num_batches // 10))
 
-  sched = LearningRateScheduler(args.learning_rate, warmup_steps=8000, decay_start_step=48000,
-                                decay_steps=24000)
+  sched = LearningRateScheduler(args.learning_rate, warmup_steps=args.warmup_steps,
+                                decay_start_step=args.decay_start_step,
+                                decay_steps=args.decay_steps)
   de.broadcast_variables(model)
   if args.fast and cuda and args.dp_input:
     from distributed_embeddings_b200.models.dlrm_fast import DLRMTrainStep
@@ -104,7 +109,11 @@ def main():
     trainer = HybridTrainer(model, lr=args.learning_rate, scheduler=sched)
     step = trainer.step
 
-  for i, (num, cat, lab) in enumerate(train):
+  def batches():
+    for _ in range(args.epochs):
+      yield from train
+
+  for i, (num, cat, lab) in enumerate(batches()):
     num, lab = num.to(device).float(), lab.to(device)
     cat = [c.to(device) for c in cat]
     if args.test_combiner:
