@@ -112,3 +112,20 @@ def test_parameter_partition_and_learning_rate():
   d.set_optimizer("sgd", lr=0.5)
   d.set_learning_rate(0.25)
   assert d._fused_optimizer["lr"] == 0.25
+
+
+def test_module_state_dict_round_trip(tmp_path):
+  """nn.Module checkpointing (per-rank shards; the sharding-independent form is get_weights /
+  save_weights): state_dict -> torch.save -> load_state_dict restores outputs exactly."""
+  torch.manual_seed(1)
+  make = lambda: dmp.DistributedEmbedding([de.Embedding(10, 4, combiner="sum"),
+                                           de.Embedding(6, 8, combiner="mean"),
+                                           de.Embedding(9, 4, combiner="sum")])
+  a, b = make(), make()
+  ids = [torch.randint(0, n, (5, 2)) for n in (10, 6, 9)]
+  assert not torch.equal(torch.cat(a(ids), 1), torch.cat(b(ids), 1))
+  path = str(tmp_path / "shard.pt")
+  torch.save(a.state_dict(), path)
+  missing = b.load_state_dict(torch.load(path))
+  assert not missing.missing_keys and not missing.unexpected_keys
+  torch.testing.assert_close(torch.cat(a(ids), 1), torch.cat(b(ids), 1), rtol=0, atol=0)
