@@ -825,3 +825,47 @@ def test_file_checkpoint_is_sharding_independent(world_save, world_load, tmp_pat
   os_missing = str(tmp_path / "nothing")
   with pytest.raises(FileNotFoundError):
     des2[0].load_weights(os_missing)
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adagrad", "adam"])
+def test_shared_learning_rate_word_is_owned_by_the_trainer(kind):
+  """A hand-scheduled trainer shares one device-resident learning-rate word with the engine
+  (``share_lr``) and zeroes it while it warms up before graph capture.  The engine's table
+  refresh - triggered in the middle of that warm-up when lazily created optimizer state appears -
+  must not re-arm the rate (regression: dense weights drifted during the warm-up of the Adagrad
+  DLRM step)."""
+  rng = np.random.default_rng(2)
+  sizes = [(30, 8), (12, 16), (50, 8)]
+  embs = [{"input_dim": r, "output_dim": w, "combiner": "sum"} for r, w in sizes]
+  world, lb = 2, 4
+  sim, des = dry_run.build_engines(embs, world, strategy="memory_balanced")
+  tables = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+  lrs = [torch.zeros(1) for _ in range(world)]
+  for r, de in enumerate(des):
+    de.set_weights(tables)
+    de.set_optimizer(kind, lr=0.5)
+    de._engine.share_lr(lrs[r])
+  ids = [rng.integers(0, r_, size=(lb * world, 2)) for r_, _ in sizes]
+  grads = [rng.standard_normal((lb * world, w)).astype(np.float32) for _, w in sizes]
+
+  def step(r):
+    sl = slice(r * lb, (r + 1) * lb)
+    out = des[r]([torch.from_numpy(i[sl]) for i in ids], concat=True)
+    out.backward(torch.from_numpy(np.concatenate([g[sl] for g in grads], 1)))
+
+  dry_run.run_ranks(sim, step)  # warm-up pass: the shared word is zero
+  assert all(float(t) == 0.0 for t in lrs), "the engine wrote a trainer-owned learning rate"
+  for got, want in zip(assemble(des), tables):
+    np.testing.assert_array_equal(got, want)
+  for t in lrs:  # the trainer arms the rate: now the tables move
+    t.fill_(0.5)
+  dry_run.run_ranks(sim, step)
+  moved = [np.abs(g - w).max() for g, w in zip(assemble(des), tables)]
+  assert min(moved) > 1e-3, moved
+  # an engine that owns its rate keeps following set_optimizer / set_learning_rate
+  sim2, des2 = dry_run.build_engines(embs, 1)
+  des2[0].set_weights(tables)
+  des2[0].set_optimizer(kind, lr=0.25)
+  dry_run.run_ranks(sim2, lambda r: des2[0]([torch.from_numpy(i[:lb]) for i in ids],
+                                            concat=True).sum().backward())
+  assert abs(float(des2[0]._engine.lr_t) - 0.25) < 1e-7
