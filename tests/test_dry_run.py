@@ -869,3 +869,53 @@ def test_shared_learning_rate_word_is_owned_by_the_trainer(kind):
   dry_run.run_ranks(sim2, lambda r: des2[0]([torch.from_numpy(i[:lb]) for i in ids],
                                             concat=True).sum().backward())
   assert abs(float(des2[0]._engine.lr_t) - 0.25) < 1e-7
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adagrad", "rowwise_adagrad", "adam"])
+def test_dry_updates_leave_tables_and_optimizer_state_untouched(kind):
+  """Graph warm-up passes of the hand-scheduled trainers run with ``dry_updates(True)``: every
+  kernel is launched, but tables, optimizer state and the step counter must come out exactly as
+  they went in - then a real step must equal a step taken without any warm-up."""
+  rng = np.random.default_rng(4)
+  sizes = [(30, 8), (12, 16), (50, 8), (21, 16)]
+  embs = [{"input_dim": r, "output_dim": w, "combiner": "sum"} for r, w in sizes]
+  world, lb = 2, 4
+  tables = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+  ids = [rng.integers(0, r_, size=(lb * world, 2)) for r_, _ in sizes]
+  grads = [rng.standard_normal((lb * world, w)).astype(np.float32) * 0.1 for _, w in sizes]
+
+  def make():
+    sim, des = dry_run.build_engines(embs, world, strategy="memory_balanced")
+    for de in des:
+      de.set_weights(tables)
+      de.set_optimizer(kind, lr=0.3)
+    return sim, des
+
+  def step(sim, des):
+    def fn(r):
+      sl = slice(r * lb, (r + 1) * lb)
+      out = des[r]([torch.from_numpy(i[sl]) for i in ids], concat=True)
+      out.backward(torch.from_numpy(np.concatenate([g[sl] for g in grads], 1)))
+    dry_run.run_ranks(sim, fn)
+
+  sim_a, des_a = make()
+  for de in des_a:
+    de._engine.dry_updates(True)
+  step(sim_a, des_a)
+  step(sim_a, des_a)
+  for got, want in zip(assemble(des_a), tables):
+    np.testing.assert_array_equal(got, want)
+  for de in des_a:
+    assert de._engine.step_count() == 0
+    for slots in de._engine.opt_state.values():
+      for k, s in enumerate(slots):
+        init = 0.1 if kind in ("adagrad", "rowwise_adagrad") else 0.0
+        assert float((s - init).abs().max()) == 0.0, (kind, k)
+    de._engine.dry_updates(False)
+  step(sim_a, des_a)
+  sim_b, des_b = make()
+  step(sim_b, des_b)
+  for a, b in zip(assemble(des_a), assemble(des_b)):
+    np.testing.assert_array_equal(a, b)
+  assert des_a[0]._engine.step_count() == des_b[0]._engine.step_count() == \
+      (0 if kind == "sgd" else 1)
