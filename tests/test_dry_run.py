@@ -919,3 +919,39 @@ def test_dry_updates_leave_tables_and_optimizer_state_untouched(kind):
     np.testing.assert_array_equal(a, b)
   assert des_a[0]._engine.step_count() == des_b[0]._engine.step_count() == \
       (0 if kind == "sgd" else 1)
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_prepared_engine_with_direct_input_views(world):
+  """The data-loader fast path: ``prepare()`` allocates the staging buffers, the loader writes
+  the ids straight into ``input_views`` (int32 here), ``run()`` does the forward without any
+  staging copy, and a second batch reuses the same buffers."""
+  rng = np.random.default_rng(8)
+  sizes = [(30, 8), (12, 16), (50, 8), (21, 4)]
+  hots = [1, 3, 2, 1]
+  embs = [{"input_dim": r, "output_dim": w, "combiner": "sum"} for r, w in sizes]
+  sim, des = dry_run.build_engines(embs, world, strategy="memory_balanced")
+  tables = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+  lb = 5
+  for de in des:
+    de.set_weights(tables)
+    de._engine.prepare(lb, hots, ids64=False)
+  ptrs = [[v.data_ptr() for v in de._engine.input_views] for de in des]
+  for batch in range(2):
+    ids = [rng.integers(0, r_, size=(lb * world, h)).astype(np.int32)
+           for (r_, _), h in zip(sizes, hots)]
+
+    def fn(r):
+      eng = des[r]._engine
+      sl = slice(r * lb, (r + 1) * lb)
+      for v, i in zip(eng.input_views, ids):
+        assert v.dtype == torch.int32 and tuple(v.shape) == i[sl].shape
+        v.copy_(torch.from_numpy(i[sl]))
+      with torch.no_grad():
+        return eng.run(concat=True).numpy().copy()
+
+    outs = dry_run.run_ranks(sim, fn)
+    exp = np.concatenate([tables[t][ids[t]].sum(1) for t in range(len(sizes))], 1)
+    for r in range(world):
+      np.testing.assert_allclose(outs[r], exp[r * lb:(r + 1) * lb], rtol=1e-5, atol=1e-5)
+    assert ptrs == [[v.data_ptr() for v in de._engine.input_views] for de in des]
