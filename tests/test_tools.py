@@ -79,3 +79,43 @@ def test_plan_report_cli():
   out = _run("tools/plan_report.py", "--tables", "1000000x128,5000x64,3000000x32", "--world", "2",
              "--column-slice-threshold", "auto", "--hbm-gib", "0.1")
   assert out.returncode == 0 and "GiB!" in out.stdout, out.stdout[-500:] + out.stderr[-500:]
+
+
+def test_critical_path_and_step_budget_on_a_synthetic_trace(tmp_path):
+  """tools/critical_path.py merges the per-rank chrome traces of `bench.py --profile-all-ranks`
+  into one timeline; tools/step_budget.py reads that text.  Two ranks, three steps each."""
+  import json
+
+  def trace(rank_delay):
+    ev, t = [], 1000.0
+    for _ in range(3):
+      t0 = t + rank_delay
+      for name, dur in (("void de::(anonymous namespace)::push_segments_kernel<int>(...)", 10),
+                        ("void de::(anonymous namespace)::lookup_fwd_kernel<int, bf16, 4>(...)", 40),
+                        ("nvjet_tst_128x256_64x6_2x2_2cta_v_bz_relubias", 30),
+                        ("void de::(anonymous namespace)::interact_fwd_kernel<128>(...)", 25),
+                        ("void de::(anonymous namespace)::allreduce_p2p_kernel<false>(...)", 20),
+                        ("void de::(anonymous namespace)::scatter_add_staged_kernel<int, bf16>(...)",
+                         35)):
+        ev.append({"ph": "X", "cat": "kernel", "name": name, "ts": t0, "dur": dur})
+        t0 += dur + 1
+      t += 400
+    return {"traceEvents": ev}
+
+  prof = str(tmp_path / "prof.txt")
+  with open(prof + ".trace.json", "w", encoding="utf-8") as f:
+    json.dump(trace(0.0), f)
+  with open(prof + ".rank1.trace.json", "w", encoding="utf-8") as f:
+    json.dump(trace(7.0), f)
+  out = _run("tools/critical_path.py", prof, "--step", "1")
+  assert out.returncode == 0, out.stderr[-1000:]
+  text = out.stdout
+  assert "== rank 0: 6 kernels" in text and "== rank 1: 6 kernels" in text
+  assert "cross-GPU waits" in text and "skew 7.0 us" in text
+  assert "last in rank 1" in text
+  timeline = tmp_path / "timeline.txt"
+  timeline.write_text(text, encoding="utf-8")
+  bud = _run("tools/step_budget.py", str(timeline))
+  assert bud.returncode == 0, bud.stderr[-1000:]
+  assert bud.stdout.count("== rank ") == 2 and "embedding lookup" in bud.stdout
+  assert "embedding update" in bud.stdout and "dense GEMM" in bud.stdout
